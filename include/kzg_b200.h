@@ -1,0 +1,167 @@
+/* kzg_b200.h — C ABI of the B200-native KZG engine (libkzg_b200.so).
+ *
+ * Drop-in boundary for the hot path of VGLoic/kzg-poly-commit-exploration:
+ * trusted-setup generation -> commit -> evaluate -> evaluation proof over BLS12-381.
+ * One FFI crossing per BULK operation (the reference crosses into blst once per group /
+ * field operation).  Citations are into the reference tree (/root/reference).
+ *
+ * Conventions
+ *   - every function returns a kzg_status (0 = OK) and never throws or aborts;
+ *     kzg_last_error(ctx) returns a message for the last failure on that ctx.
+ *   - canonical encodings only: Fr = 32 bytes little-endian (inputs >= r are reduced mod r,
+ *     as Scalar::from_le_bytes does, src/scalar.rs:54-61); G1 = 48-byte compressed ZCash
+ *     format (Serialize for G1Point, src/curves.rs:99-110).
+ *   - pointers are HOST pointers unless the parameter name ends in _dev (device pointers in
+ *     the ctx's CUDA device, e.g. a torch tensor's data_ptr()).
+ *   - a kzg_ctx is bound to ONE CUDA device and is externally synchronised (one caller at a
+ *     time).  Multi-GPU = one process (or ctx) per GPU; partial results are exchanged by the
+ *     host (NCCL all-gather of kzg_g1_partial blobs) and folded with kzg_g1_combine.
+ *   - there is NO CPU fallback for bulk operations: without a CUDA device kzg_ctx_create
+ *     fails with KZG_E_CUDA.  The kzg_fr_* / kzg_g1_* single-element helpers are host code
+ *     (they replace per-element blst calls of the public Rust API, not the hot path).
+ */
+#ifndef KZG_B200_H
+#define KZG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kzg_ctx kzg_ctx;     /* device, streams, scratch arenas                        */
+typedef struct kzg_setup kzg_setup; /* device-resident G1 powers of tau (+ precomputed tables) */
+
+typedef enum {
+  KZG_OK = 0,
+  KZG_E_DEGREE_TOO_HIGH = 1,   /* Polynomial::commit, src/polynomial.rs:201-205            */
+  KZG_E_CONSTANT_POLY = 2,     /* divide_by_root, src/polynomial.rs:159-166                */
+  KZG_E_REMAINDER_NONZERO = 3, /* divide_by_root, src/polynomial.rs:188-192                */
+  KZG_E_BAD_POINT = 4,         /* bytes_to_blst_p1, src/curves.rs:131-137                  */
+  KZG_E_BAD_LENGTH = 5,        /* src/curves.rs:120-125, src/scalar.rs:249-270             */
+  KZG_E_SETUP_TOO_SHORT = 6,   /* verify_proof indexes setup[1], src/polynomial.rs:284     */
+  KZG_E_BAD_ARG = 7,
+  KZG_E_CUDA = 100,
+  KZG_E_NOMEM = 102
+} kzg_status;
+
+/* size of an exported partial G1 sum (XYZZ, Montgomery limbs) used between GPUs */
+#define KZG_G1_PARTIAL_BYTES 192
+
+/* ---- context ------------------------------------------------------------------------- */
+int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id);
+void kzg_ctx_destroy(kzg_ctx* ctx);
+const char* kzg_last_error(const kzg_ctx* ctx);
+const char* kzg_status_string(int32_t status);
+/* block until all work queued on the ctx stream has finished */
+int32_t kzg_ctx_sync(kzg_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx);
+/* device time of the last bulk call's dominant kernel(s) in ms, measured with CUDA events on
+ * the ctx stream: which = 0 bucket accumulate / fixed-base accumulate, 1 whole call */
+float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which);
+/* tuning: window bits for the bucket MSM (0 = auto) and for the fixed-base batch tables */
+int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value);
+
+/* ---- trusted setup: SetupArtifactsGenerator::new(secret).take(n) ---------------------
+ * src/trusted_setup.rs:20-28,40-78.  Item i = [s^i]G1 with s = secret_be mod r; item 0 is
+ * the generator whatever s is.  `first` lets a rank generate only items first..first+n
+ * (index-range sharding); the setup then holds those n items as its bases 0..n. */
+int32_t kzg_setup_generate(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t first, uint64_t n,
+                           kzg_setup** out);
+/* Deserialize for G1Point x n (src/curves.rs:112-183): 48-byte compressed points, on-curve
+ * check, no subgroup check; KZG_E_BAD_POINT on the first malformed entry. */
+int32_t kzg_setup_import_g1(kzg_ctx* ctx, const uint8_t* g1_c48, uint64_t n, kzg_setup** out);
+/* Serialize for G1Point x count (src/curves.rs:99-110) */
+int32_t kzg_setup_export_g1(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count,
+                            uint8_t* out_c48);
+uint64_t kzg_setup_len(const kzg_setup* s);
+void kzg_setup_destroy(kzg_setup* s);
+/* Precompute per-base tables once per setup (amortised over every later commit):
+ *   kzg_setup_prepare_msm  : 2^(c*j) * P_i for all windows j (folds every Pippenger window
+ *                            into one bucket set; c = window_bits, 0 = auto from n)
+ *   kzg_setup_prepare_fixed: d * 2^(c*j) * P_i, d = 1..2^(c-1), for the first n_points bases
+ *                            (bucket-free fixed-base commit used for blob batches)           */
+int32_t kzg_setup_prepare_msm(kzg_ctx* ctx, kzg_setup* s, int32_t window_bits);
+int32_t kzg_setup_prepare_fixed(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int32_t window_bits);
+
+/* ---- commit / evaluate / open ----------------------------------------------------------
+ * Coefficients: n x 32-byte LE, ascending degree; trailing zero coefficients are trimmed as
+ * Polynomial::try_from does (src/polynomial.rs:55-75).                                      */
+/* Polynomial::commit (src/polynomial.rs:200-215) */
+int32_t kzg_commit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n,
+                   uint8_t out_c48[48]);
+/* Polynomial::evaluate (src/polynomial.rs:112-123) */
+int32_t kzg_evaluate(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
+                     uint8_t y_le[32]);
+/* sub + divide_by_root (src/polynomial.rs:128-195): q = (p - y)/(x - z); q_len receives the
+ * trimmed length (n-1 untrimmed values are written).  y_le == NULL means "use p(z)". */
+int32_t kzg_quotient(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
+                     const uint8_t* y_le, uint8_t* q_le32, uint64_t* q_len);
+/* Evaluation::generate_proof (src/polynomial.rs:260-269).  If y_expected_le is given and
+ * differs from p(z): KZG_E_REMAINDER_NONZERO (KZG_E_CONSTANT_POLY for a constant polynomial),
+ * mirroring divide_by_root's errors. */
+int32_t kzg_open(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n,
+                 const uint8_t z_le[32], const uint8_t* y_expected_le, uint8_t y_out_le[32],
+                 uint8_t proof_c48[48]);
+/* plain G1 MSM over the first n bases, no trimming semantics (BASELINE config C3) */
+int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n,
+                   uint8_t out_c48[48]);
+
+/* ---- blob batches (BASELINE config C4): `blobs` polynomials of n coefficients each ------ */
+int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32,
+                         uint64_t blobs, uint64_t n, uint8_t* out_c48);
+int32_t kzg_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32,
+                       uint64_t blobs, uint64_t n, const uint8_t* z_le32, uint8_t* y_le32,
+                       uint8_t* proofs_c48);
+
+/* ---- device-resident variants (inputs already in HBM; results still land on the host) --- */
+int32_t kzg_msm_g1_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,
+                       uint8_t out_c48[48]);
+/* partial sum of a shard, left on the device as a KZG_G1_PARTIAL_BYTES blob (for all-gather) */
+int32_t kzg_msm_g1_partial_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev,
+                               uint64_t n, void* partial_dev);
+/* fold `count` partial sums (device) into one compressed point */
+int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count,
+                           uint8_t out_c48[48]);
+int32_t kzg_commit_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev,
+                             uint64_t blobs, uint64_t n, void* out_c48_dev);
+int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev,
+                           uint64_t blobs, uint64_t n, const void* z_dev, void* y_dev,
+                           void* proofs_c48_dev);
+int32_t kzg_evaluate_dev(kzg_ctx* ctx, const void* coeffs_dev, uint64_t n, const uint8_t z_le[32],
+                         uint8_t y_le[32]);
+
+/* ---- single-element host helpers (public per-element Rust API; not the hot path) -------- */
+/* Scalar::mul/add/sub/neg/pow (src/scalar.rs:111-223) on canonical 32-byte LE values */
+void kzg_fr_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+void kzg_fr_add(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+void kzg_fr_sub(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+void kzg_fr_neg(const uint8_t a[32], uint8_t out[32]);
+void kzg_fr_pow(const uint8_t a[32], uint64_t n, uint8_t out[32]);
+/* Scalar::from_le_bytes reduction (src/scalar.rs:54-61) */
+void kzg_fr_reduce(const uint8_t a[32], uint8_t out[32]);
+/* G1Point::add/sub/mult/from_scalar (src/curves.rs:50-96) on 48-byte compressed points */
+int32_t kzg_g1_add(const uint8_t a[48], const uint8_t b[48], uint8_t out[48]);
+int32_t kzg_g1_sub(const uint8_t a[48], const uint8_t b[48], uint8_t out[48]);
+int32_t kzg_g1_mul(const uint8_t p[48], const uint8_t k_le[32], uint8_t out[48]);
+void kzg_g1_from_scalar(const uint8_t k_le[32], uint8_t out[48]);
+/* on-curve / encoding check of one compressed point: KZG_OK or KZG_E_BAD_POINT */
+int32_t kzg_g1_check(const uint8_t p[48]);
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+/* integer-pipe roofline probe: independent 32x32+64 multiply-add chains on every SM;
+ * returns wide multiply-adds per second (BASELINE.md §4 "measured integer peak") */
+int32_t kzg_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s);
+/* sustained Montgomery Fq multiplications per second of the shipped field kernel (all SMs busy) */
+int32_t kzg_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s);
+/* field self-test on the device: n Montgomery products a*b for a_i = U(seed,2i), b_i = U(seed,2i+1)
+ * reduced into the field; writes canonical results (48 or 32 bytes LE each) for the oracle */
+int32_t kzg_selftest_fq_mul(kzg_ctx* ctx, const uint8_t* a_le48, const uint8_t* b_le48, uint64_t n,
+                            uint8_t* out_le48);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KZG_B200_H */

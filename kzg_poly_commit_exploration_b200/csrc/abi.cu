@@ -1,0 +1,483 @@
+// extern "C" boundary of libkzg_b200.so (include/kzg_b200.h): context, setup objects and the bulk
+// operations.  Semantics (trimming, error cases) mirror the reference's public API:
+//   Polynomial::try_from / degree / commit / evaluate / sub / divide_by_root  src/polynomial.rs:38-215
+//   Evaluation::generate_proof                                                 src/polynomial.rs:260-269
+//   SetupArtifactsGenerator                                                    src/trusted_setup.rs:20-78
+// There is no CPU fallback for any bulk operation.
+#include <algorithm>
+#include <cstring>
+#include "engine.cuh"
+
+using namespace kzg;
+
+namespace kzg {
+
+int32_t scratch_get(kzg_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->scratch_cap[slot] < bytes) {
+    if (ctx->scratch[slot]) {
+      KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->scratch[slot]);
+      ctx->scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0;
+    }
+    size_t cap = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+    cudaError_t e = cudaMalloc(&ctx->scratch[slot], cap);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ctx->err = "cudaMalloc(scratch): " + std::string(cudaGetErrorString(e));
+      return KZG_E_NOMEM;
+    }
+    ctx->scratch_cap[slot] = cap;
+  }
+  *out = ctx->scratch[slot];
+  return KZG_OK;
+}
+
+int32_t pinned_get(kzg_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->pinned_cap < bytes) {
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr; ctx->pinned_cap = 0;
+    KZG_CUDA_OK(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_cap = bytes;
+  }
+  *out = ctx->pinned;
+  return KZG_OK;
+}
+
+}  // namespace kzg
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// value == 0 mod r  <=>  value in {0, r, 2r} (2^256 < 3r)
+bool le32_is_zero_mod_r(const uint8_t* b) {
+  Fr a; fr_load_le(a, b); fr_canon_reduce(a);
+  return is_zero(a);
+}
+// Polynomial::try_from trimming (src/polynomial.rs:63-72): number of coefficients up to the last
+// non-zero one; 0 when every coefficient is zero (the reference keeps one zero coefficient then,
+// which evaluates / commits identically to none).
+uint64_t trimmed_len(const uint8_t* coeffs, uint64_t n) {
+  while (n > 0 && le32_is_zero_mod_r(coeffs + (n - 1) * 32)) n--;
+  return n;
+}
+
+int32_t ensure_msm_table(kzg_ctx* ctx, const kzg_setup* s) {
+  if (s->msm_tab) return KZG_OK;
+  return build_msm_table(ctx, const_cast<kzg_setup*>(s), 0);
+}
+
+// one MSM over the first n bases with device scalars -> XYZZ on device
+int32_t msm_any(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n, G1Xyzz* out_dev) {
+  if (s->fix_tab && n <= s->fix_n && n > 0) return msm_fixed_batch(ctx, s, scalars_dev, 1, n, n, out_dev);
+  KZG_TRY(ensure_msm_table(ctx, s));
+  return msm_bucket(ctx, s, scalars_dev, n, out_dev);
+}
+
+int32_t finish_one(kzg_ctx* ctx, const G1Xyzz* pt_dev, uint8_t out_c48[48]) {
+  void* o;
+  KZG_TRY(scratch_get(ctx, SCR_OUT, 256, &o));
+  KZG_TRY(finalize_points(ctx, pt_dev, 1, reinterpret_cast<uint8_t*>(o)));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c48, o, 48, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return KZG_OK;
+}
+
+void update_timers(kzg_ctx* ctx) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[0] = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->last_ms[1] = ms;
+  cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id) {
+  if (!out) return KZG_E_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device_id < 0 || device_id >= count) {
+    cudaGetLastError();
+    return KZG_E_CUDA;  // no CPU fallback: the engine needs a CUDA device
+  }
+  kzg_ctx* ctx = new kzg_ctx();
+  ctx->device = device_id;
+  if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
+  for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 4; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  cudaStreamSynchronize(ctx->stream);
+  *out = ctx;
+  return KZG_OK;
+}
+
+void kzg_ctx_destroy(kzg_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < SCR_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->gtable) cudaFree(ctx->gtable);
+  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* kzg_last_error(const kzg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int32_t kzg_ctx_sync(kzg_ctx* ctx) {
+  DeviceGuard g(ctx->device);
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  update_timers(ctx);
+  return KZG_OK;
+}
+
+uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) { return ctx->launches; }
+
+float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which) {
+  return (which == 0 || which == 1) ? ctx->last_ms[which] : 0.f;
+}
+
+int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
+  std::string n(name ? name : "");
+  if (n == "msm_window_bits") ctx->opt_msm_window = (int)value;
+  else if (n == "fixed_window_bits") ctx->opt_fixed_window = (int)value;
+  else if (n == "reduce_chunk") ctx->opt_reduce_chunk = (int)value;
+  else if (n == "heavy_cap") ctx->opt_heavy_cap = (int)std::max<int64_t>(1, value);
+  else return fail(ctx, KZG_E_BAD_ARG, "unknown option");
+  return KZG_OK;
+}
+
+// ---- setup ---------------------------------------------------------------------------------
+static int32_t setup_alloc(kzg_ctx* ctx, uint64_t n, kzg_setup** out) {
+  kzg_setup* s = new kzg_setup();
+  s->ctx = ctx; s->n = n;
+  if (n) {
+    cudaError_t e = cudaMalloc(&s->bases, n * sizeof(G1Affine));
+    if (e != cudaSuccess) { cudaGetLastError(); delete s; return fail(ctx, KZG_E_NOMEM, "cudaMalloc(bases)"); }
+  }
+  *out = s;
+  return KZG_OK;
+}
+
+int32_t kzg_setup_generate(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t first, uint64_t n, kzg_setup** out) {
+  if (!ctx || !secret_be || !out) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  kzg_setup* s = nullptr;
+  KZG_TRY(setup_alloc(ctx, n, &s));
+  int32_t st = setup_generate_dev(ctx, secret_be, first, n, s->bases);
+  if (st == KZG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, KZG_E_CUDA, "sync after setup generation");
+  if (st != KZG_OK) { kzg_setup_destroy(s); return st; }
+  *out = s;
+  return KZG_OK;
+}
+
+int32_t kzg_setup_import_g1(kzg_ctx* ctx, const uint8_t* g1_c48, uint64_t n, kzg_setup** out) {
+  if (!ctx || (!g1_c48 && n) || !out) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  kzg_setup* s = nullptr;
+  KZG_TRY(setup_alloc(ctx, n, &s));
+  int32_t st = KZG_OK;
+  if (n) {
+    void* in;
+    st = scratch_get(ctx, SCR_SCALARS, n * 48, &in);
+    if (st == KZG_OK && cudaMemcpyAsync(in, g1_c48, n * 48, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+      st = fail(ctx, KZG_E_CUDA, "H2D compressed points");
+    int bad = -1;
+    if (st == KZG_OK) st = uncompress_points(ctx, reinterpret_cast<uint8_t*>(in), n, s->bases, &bad);
+    if (st == KZG_OK && bad >= 0) {
+      ctx->err = "Got error while uncompressing: point " + std::to_string(bad);
+      st = KZG_E_BAD_POINT;
+    }
+  }
+  if (st != KZG_OK) { kzg_setup_destroy(s); return st; }
+  *out = s;
+  return KZG_OK;
+}
+
+int32_t kzg_setup_export_g1(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count, uint8_t* out_c48) {
+  if (!ctx || !s || first + count > s->n) return fail(ctx, KZG_E_BAD_ARG, "export range outside the setup");
+  if (count == 0) return KZG_OK;
+  DeviceGuard g(ctx->device);
+  void* o;
+  KZG_TRY(scratch_get(ctx, SCR_OUT, count * 48, &o));
+  KZG_TRY(compress_points(ctx, s->bases + first, count, reinterpret_cast<uint8_t*>(o)));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c48, o, count * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return KZG_OK;
+}
+
+uint64_t kzg_setup_len(const kzg_setup* s) { return s ? s->n : 0; }
+
+void kzg_setup_destroy(kzg_setup* s) {
+  if (!s) return;
+  DeviceGuard g(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  if (s->bases) cudaFree(s->bases);
+  if (s->msm_tab) cudaFree(s->msm_tab);
+  if (s->fix_tab) cudaFree(s->fix_tab);
+  delete s;
+}
+
+int32_t kzg_setup_prepare_msm(kzg_ctx* ctx, kzg_setup* s, int32_t window_bits) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  return build_msm_table(ctx, s, window_bits);
+}
+
+int32_t kzg_setup_prepare_fixed(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int32_t window_bits) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  return build_fixed_table(ctx, s, n_points, window_bits);
+}
+
+// ---- single-polynomial operations ----------------------------------------------------------------
+int32_t kzg_msm_g1_partial_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, void* partial_dev) {
+  if (!ctx || !s || !partial_dev) return KZG_E_BAD_ARG;
+  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  DeviceGuard g(ctx->device);
+  return msm_any(ctx, s, reinterpret_cast<const uint8_t*>(scalars_dev), n, reinterpret_cast<G1Xyzz*>(partial_dev));
+}
+
+int32_t kzg_msm_g1_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]) {
+  if (!ctx || !s || !out_c48) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  void* r;
+  KZG_TRY(scratch_get(ctx, SCR_MISC, 1024, &r));
+  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
+  KZG_TRY(kzg_msm_g1_partial_dev(ctx, s, scalars_dev, n, res));
+  KZG_TRY(finish_one(ctx, res, out_c48));
+  update_timers(ctx);
+  return KZG_OK;
+}
+
+int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, uint8_t out_c48[48]) {
+  if (!ctx || !s || (!scalars_le32 && n) || !out_c48) return KZG_E_BAD_ARG;
+  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  DeviceGuard g(ctx->device);
+  void* d;
+  KZG_TRY(scratch_get(ctx, SCR_SCALARS, n * 32, &d));
+  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, scalars_le32, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return kzg_msm_g1_dev(ctx, s, d, n, out_c48);
+}
+
+int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count, uint8_t out_c48[48]) {
+  if (!ctx || (!partials_dev && count) || !out_c48) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  void* r;
+  KZG_TRY(scratch_get(ctx, SCR_MISC, 1024, &r));
+  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
+  KZG_TRY(sum_points(ctx, reinterpret_cast<const G1Xyzz*>(partials_dev), count, res));
+  return finish_one(ctx, res, out_c48);
+}
+
+int32_t kzg_commit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n, uint8_t out_c48[48]) {
+  if (!ctx || !s || (!coeffs_le32 && n) || !out_c48) return KZG_E_BAD_ARG;
+  uint64_t nt = trimmed_len(coeffs_le32, n);
+  // (degree() + 1) > setup.len()  with degree() == 0 for the empty / zero polynomial (src/polynomial.rs:95-100,201)
+  if (std::max<uint64_t>(nt, 1) > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  return kzg_msm_g1(ctx, s, coeffs_le32, nt, out_c48);
+}
+
+int32_t kzg_evaluate_dev(kzg_ctx* ctx, const void* coeffs_dev, uint64_t n, const uint8_t z_le[32], uint8_t y_le[32]) {
+  if (!ctx || (!coeffs_dev && n) || !z_le || !y_le) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  void* m;
+  KZG_TRY(scratch_get(ctx, SCR_FR_B, 256, &m));
+  uint8_t* zd = reinterpret_cast<uint8_t*>(m);
+  uint8_t* yd = zd + 64;
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le, 32, cudaMemcpyHostToDevice, ctx->stream));
+  KZG_TRY(poly_eval_quotient(ctx, reinterpret_cast<const uint8_t*>(coeffs_dev), 1, n, zd, yd, nullptr));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le, yd, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return KZG_OK;
+}
+
+int32_t kzg_evaluate(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], uint8_t y_le[32]) {
+  if (!ctx || (!coeffs_le32 && n) || !z_le || !y_le) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  void* d;
+  KZG_TRY(scratch_get(ctx, SCR_SCALARS, n * 32, &d));
+  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return kzg_evaluate_dev(ctx, d, n, z_le, y_le);
+}
+
+// shared by kzg_quotient / kzg_open: stages coefficients, runs the scan, applies the reference's
+// divide_by_root error rules.  On success *q_dev holds nt-1 (or 0) canonical coefficients.
+static int32_t quotient_core(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
+                             const uint8_t* y_le, uint8_t y_out[32], uint8_t** q_dev, uint64_t* q_len) {
+  uint64_t nt = trimmed_len(coeffs_le32, n);
+  void *d, *m, *q;
+  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(nt, 1) * 32, &d));
+  KZG_TRY(scratch_get(ctx, SCR_QUOT, std::max<uint64_t>(nt, 1) * 32, &q));
+  KZG_TRY(scratch_get(ctx, SCR_FR_B, 256, &m));
+  uint8_t* zd = reinterpret_cast<uint8_t*>(m);
+  uint8_t* yd = zd + 64;
+  if (nt) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, nt * 32, cudaMemcpyHostToDevice, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le, 32, cudaMemcpyHostToDevice, ctx->stream));
+  KZG_TRY(poly_eval_quotient(ctx, reinterpret_cast<uint8_t*>(d), 1, nt, zd, yd, reinterpret_cast<uint8_t*>(q)));
+  uint8_t y_dev_val[32];
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_dev_val, yd, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (y_out) memcpy(y_out, y_dev_val, 32);
+  bool y_matches = true;
+  if (y_le) {
+    uint8_t yr[32];
+    kzg_fr_reduce(y_le, yr);
+    y_matches = memcmp(yr, y_dev_val, 32) == 0;
+  }
+  if (nt <= 1) {
+    // p - y is a constant: zero -> empty quotient, otherwise "Unable to divide a constant polynomial"
+    if (!y_matches) return fail(ctx, KZG_E_CONSTANT_POLY, kzg_status_string(KZG_E_CONSTANT_POLY));
+    *q_len = 0;
+  } else {
+    if (!y_matches) return fail(ctx, KZG_E_REMAINDER_NONZERO, kzg_status_string(KZG_E_REMAINDER_NONZERO));
+    *q_len = nt - 1;
+  }
+  *q_dev = reinterpret_cast<uint8_t*>(q);
+  return KZG_OK;
+}
+
+int32_t kzg_quotient(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
+                     const uint8_t* y_le, uint8_t* q_le32, uint64_t* q_len) {
+  if (!ctx || (!coeffs_le32 && n) || !z_le || !q_len) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  uint8_t* qd = nullptr;
+  KZG_TRY(quotient_core(ctx, coeffs_le32, n, z_le, y_le, nullptr, &qd, q_len));
+  if (*q_len && q_le32) {
+    KZG_CUDA_OK(ctx, cudaMemcpyAsync(q_le32, qd, *q_len * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return KZG_OK;
+}
+
+int32_t kzg_open(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
+                 const uint8_t* y_expected_le, uint8_t y_out_le[32], uint8_t proof_c48[48]) {
+  if (!ctx || !s || (!coeffs_le32 && n) || !z_le || !proof_c48) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  uint8_t* qd = nullptr;
+  uint64_t ql = 0;
+  KZG_TRY(quotient_core(ctx, coeffs_le32, n, z_le, y_expected_le, y_out_le, &qd, &ql));
+  if (std::max<uint64_t>(ql, 1) > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  return kzg_msm_g1_dev(ctx, s, qd, ql, proof_c48);
+}
+
+// ---- blob batches ------------------------------------------------------------------------------------
+static int32_t batch_points_out(kzg_ctx* ctx, const G1Xyzz* pts, uint64_t blobs, uint8_t* out_c48_dev) {
+  void* aff;
+  KZG_TRY(scratch_get(ctx, SCR_BATCH_AFF, blobs * sizeof(G1Affine), &aff));
+  KZG_TRY(batch_to_affine(ctx, pts, blobs, reinterpret_cast<G1Affine*>(aff)));
+  return compress_points(ctx, reinterpret_cast<G1Affine*>(aff), blobs, out_c48_dev);
+}
+
+static int32_t msm_batch_any(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t blobs, uint64_t n,
+                             uint64_t stride, G1Xyzz* out) {
+  if (s->fix_tab && n <= s->fix_n) return msm_fixed_batch(ctx, s, scalars_dev, blobs, n, stride, out);
+  KZG_TRY(ensure_msm_table(ctx, s));
+  for (uint64_t b = 0; b < blobs; b++) KZG_TRY(msm_bucket(ctx, s, scalars_dev + b * stride * 32, n, out + b));
+  return KZG_OK;
+}
+
+int32_t kzg_commit_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n,
+                             void* out_c48_dev) {
+  if (!ctx || !s || (!coeffs_dev && blobs * n) || !out_c48_dev) return KZG_E_BAD_ARG;
+  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  if (blobs == 0) return KZG_OK;
+  DeviceGuard g(ctx->device);
+  void* pts;
+  KZG_TRY(scratch_get(ctx, SCR_BATCH_PTS, blobs * sizeof(G1Xyzz), &pts));
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  KZG_TRY(msm_batch_any(ctx, s, reinterpret_cast<const uint8_t*>(coeffs_dev), blobs, n, n, reinterpret_cast<G1Xyzz*>(pts)));
+  KZG_TRY(batch_points_out(ctx, reinterpret_cast<G1Xyzz*>(pts), blobs, reinterpret_cast<uint8_t*>(out_c48_dev)));
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  return KZG_OK;
+}
+
+int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n,
+                           const void* z_dev, void* y_dev, void* proofs_c48_dev) {
+  if (!ctx || !s || (!coeffs_dev && blobs * n) || !z_dev || !y_dev || !proofs_c48_dev) return KZG_E_BAD_ARG;
+  if (n > s->n + 1) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  if (blobs == 0) return KZG_OK;
+  DeviceGuard g(ctx->device);
+  void *pts, *q;
+  KZG_TRY(scratch_get(ctx, SCR_BATCH_PTS, blobs * sizeof(G1Xyzz), &pts));
+  KZG_TRY(scratch_get(ctx, SCR_QUOT, std::max<uint64_t>(blobs * n, 1) * 32, &q));
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  KZG_TRY(poly_eval_quotient(ctx, reinterpret_cast<const uint8_t*>(coeffs_dev), blobs, n, reinterpret_cast<const uint8_t*>(z_dev),
+                             reinterpret_cast<uint8_t*>(y_dev), reinterpret_cast<uint8_t*>(q)));
+  uint64_t nq = n ? n - 1 : 0;
+  KZG_TRY(msm_batch_any(ctx, s, reinterpret_cast<uint8_t*>(q), blobs, nq, n, reinterpret_cast<G1Xyzz*>(pts)));
+  KZG_TRY(batch_points_out(ctx, reinterpret_cast<G1Xyzz*>(pts), blobs, reinterpret_cast<uint8_t*>(proofs_c48_dev)));
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  return KZG_OK;
+}
+
+static uint64_t batch_max_trimmed(const uint8_t* coeffs, uint64_t blobs, uint64_t n) {
+  uint64_t m = 0;
+  for (uint64_t b = 0; b < blobs; b++) m = std::max(m, trimmed_len(coeffs + b * n * 32, n));
+  return m;
+}
+
+int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n,
+                         uint8_t* out_c48) {
+  if (!ctx || !s || (!coeffs_le32 && blobs * n) || !out_c48) return KZG_E_BAD_ARG;
+  if (blobs == 0) return KZG_OK;
+  if (std::max<uint64_t>(n, 1) > s->n && std::max<uint64_t>(batch_max_trimmed(coeffs_le32, blobs, n), 1) > s->n)
+    return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  if (n > s->n) return fail(ctx, KZG_E_BAD_ARG, "batch with trailing-zero padding beyond the setup is not supported");
+  DeviceGuard g(ctx->device);
+  void *d, *o;
+  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(blobs * n, 1) * 32, &d));
+  KZG_TRY(scratch_get(ctx, SCR_OUT, blobs * 48, &o));
+  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, blobs * n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  KZG_TRY(kzg_commit_batch_dev(ctx, s, d, blobs, n, o));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c48, o, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  update_timers(ctx);
+  return KZG_OK;
+}
+
+int32_t kzg_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n,
+                       const uint8_t* z_le32, uint8_t* y_le32, uint8_t* proofs_c48) {
+  if (!ctx || !s || (!coeffs_le32 && blobs * n) || !z_le32 || !y_le32 || !proofs_c48) return KZG_E_BAD_ARG;
+  if (blobs == 0) return KZG_OK;
+  DeviceGuard g(ctx->device);
+  void *d, *o, *zy;
+  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(blobs * n, 1) * 32, &d));
+  KZG_TRY(scratch_get(ctx, SCR_OUT, blobs * 48, &o));
+  KZG_TRY(scratch_get(ctx, SCR_FR_A, blobs * 64, &zy));
+  uint8_t* zd = reinterpret_cast<uint8_t*>(zy);
+  uint8_t* yd = zd + blobs * 32;
+  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, blobs * n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le32, blobs * 32, cudaMemcpyHostToDevice, ctx->stream));
+  KZG_TRY(kzg_open_batch_dev(ctx, s, d, blobs, n, zd, yd, o));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le32, yd, blobs * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(proofs_c48, o, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  update_timers(ctx);
+  return KZG_OK;
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------------
+int32_t kzg_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s) {
+  if (!ctx || !wide_mac_per_s) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  return probe_imad(ctx, wide_mac_per_s);
+}
+
+int32_t kzg_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s) {
+  if (!ctx || !fq_mul_per_s) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  return probe_fq_mul(ctx, fq_mul_per_s);
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// Internal engine declarations shared by the .cu translation units of libkzg_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/kzg_b200.h"
+#include "g1.cuh"
+
+namespace kzg {
+
+enum ScratchSlot {
+  SCR_SCALARS = 0,   // staged scalars / coefficients (host -> device)
+  SCR_KEYS_A, SCR_KEYS_B, SCR_VALS_A, SCR_VALS_B, SCR_SORT_TMP,
+  SCR_BUCKET_START, SCR_BUCKETS, SCR_RED_A, SCR_RED_B, SCR_HEAVY,
+  SCR_XYZZ_TMP, SCR_PREFIX, SCR_QUOT, SCR_SEG, SCR_OUT, SCR_MISC, SCR_FR_A, SCR_FR_B,
+  SCR_BATCH_PTS, SCR_BATCH_AFF,
+  SCR_COUNT
+};
+
+}  // namespace kzg
+
+struct kzg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_ms[2] = {0.f, 0.f};
+  void* scratch[kzg::SCR_COUNT] = {};
+  size_t scratch_cap[kzg::SCR_COUNT] = {};
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  kzg::G1Affine* gtable = nullptr;     // [16][32768] multiples of the generator (setup generation)
+  int opt_msm_window = 0;              // 0 = auto
+  int opt_fixed_window = 0;            // 0 = auto
+  int opt_reduce_chunk = 16;
+  int opt_heavy_cap = 1024;
+  int sm_count = 148;
+};
+
+struct kzg_setup {
+  kzg_ctx* ctx = nullptr;
+  uint64_t n = 0;
+  kzg::G1Affine* bases = nullptr;      // [n] affine Montgomery, (0,0) = infinity
+  // folded-window table for the bucket MSM: tab[j*n + i] = 2^(c*j) * P_i ; tab window 0 == bases
+  int msm_c = 0, msm_w = 0;
+  kzg::G1Affine* msm_tab = nullptr;    // [(w) * n]  (window 0 aliases nothing: full copy kept for simple indexing)
+  // fixed-base lookup table: fix[((i*w + j) << (c-1)) + d-1] = d * 2^(c*j) * P_i
+  int fix_c = 0, fix_w = 0;
+  uint64_t fix_n = 0;
+  kzg::G1Affine* fix_tab = nullptr;
+};
+
+namespace kzg {
+
+#define KZG_CUDA_OK(ctx, call)                                                              \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                     \
+      return (e__ == cudaErrorMemoryAllocation) ? KZG_E_NOMEM : KZG_E_CUDA;                 \
+    }                                                                                       \
+  } while (0)
+
+#define KZG_TRY(expr)                    \
+  do {                                   \
+    int32_t st__ = (expr);               \
+    if (st__ != KZG_OK) return st__;     \
+  } while (0)
+
+// count + check a kernel launch
+#define KZG_LAUNCHED(ctx)                                   \
+  do {                                                      \
+    (ctx)->launches++;                                      \
+    KZG_CUDA_OK(ctx, cudaGetLastError());                   \
+  } while (0)
+
+int32_t scratch_get(kzg_ctx* ctx, int slot, size_t bytes, void** out);
+int32_t pinned_get(kzg_ctx* ctx, size_t bytes, void** out);
+inline int32_t fail(kzg_ctx* ctx, int32_t st, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return st;
+}
+
+// ---- window geometry ------------------------------------------------------------------
+inline int windows_for(int c) { return (256 + c - 1) / c; }
+// signed-digit recoding needs the top window to absorb a carry: with r < 2^255 and
+// W = ceil(256/c) windows the top window holds at most (255 - c*(W-1)) < c bits, so the
+// carry never leaves it.
+int auto_msm_window(uint64_t n);
+
+// ---- poly.cu (K4: Horner evaluation + quotient scan) -----------------------------------
+// coeffs_dev: blobs x n x 32 B canonical-or-not LE; z_dev: blobs x 32 B; outputs canonical.
+// q_dev may be null (evaluate only). y_dev: blobs x 32 B.
+int32_t poly_eval_quotient(kzg_ctx* ctx, const uint8_t* coeffs_dev, uint64_t blobs, uint64_t n,
+                           const uint8_t* z_dev, uint8_t* y_dev, uint8_t* q_dev);
+
+// ---- setup.cu (K3) -------------------------------------------------------------------------
+int32_t setup_generate_dev(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t first, uint64_t n,
+                           G1Affine* bases_dev);
+int32_t batch_to_affine(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t n, G1Affine* out_dev);
+int32_t compress_points(kzg_ctx* ctx, const G1Affine* in_dev, uint64_t n, uint8_t* out_dev);
+int32_t uncompress_points(kzg_ctx* ctx, const uint8_t* in_dev, uint64_t n, G1Affine* out_dev, int* bad_index);
+int32_t build_msm_table(kzg_ctx* ctx, kzg_setup* s, int c);
+int32_t build_fixed_table(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int c);
+
+// ---- msm.cu (K2) -----------------------------------------------------------------------------
+// result_dev: one G1Xyzz (device).  Uses s->msm_tab (built on demand).
+int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
+                   G1Xyzz* result_dev);
+// sum `count` XYZZ points (device) into out_dev[0]
+int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev);
+// XYZZ (device) x count -> 48-byte compressed (device)
+int32_t finalize_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, uint8_t* out_c48_dev);
+
+// ---- batch.cu (K5) ---------------------------------------------------------------------------
+// blobs MSMs of n scalars each against the fixed-base table; out: blobs XYZZ
+int32_t msm_fixed_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t blobs,
+                        uint64_t n, uint64_t stride_scalars, G1Xyzz* out_dev);
+
+// ---- probe.cu --------------------------------------------------------------------------------
+int32_t probe_imad(kzg_ctx* ctx, double* wide_mac_per_s);
+int32_t probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s);
+
+}  // namespace kzg

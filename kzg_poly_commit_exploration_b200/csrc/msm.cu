@@ -1,0 +1,278 @@
+// K2 — Pippenger G1 multi-scalar multiplication (the commit / open hot loop).
+//
+// Replaces Polynomial::commit's loop (src/polynomial.rs:207-212): n x (256-bit blst_p1_mult +
+// blst_p1_add_or_double), i.e. O(255 n) group operations, by
+//   1. recode   : canonical scalar -> W = ceil(256/c) signed c-bit digits; digit d of
+//                 window j for point i becomes the pair (bucket |d|-1, table index j*n+i | sign).
+//                 Windows are FOLDED: the setup holds 2^(c j) * P_i for every j (built once per
+//                 setup, setup.cu), so all W windows share one set of 2^(c-1) buckets and the
+//                 per-window reduction + c doublings per window disappear.
+//   2. sort     : radix sort of the (bucket, index) pairs (cub::DeviceRadixSort, c key bits).
+//   3. bounds   : bucket b owns sorted entries [start[b], start[b+1]).
+//   4. accumulate: one thread per bucket, XYZZ += affine (8M+2S), table points fetched with
+//                 128-bit loads; buckets above `heavy_cap` entries (adversarial inputs: all-equal
+//                 scalars) go to a block-per-bucket kernel with a shared-memory tree.
+//   5. reduce   : sum_b (b+1) * B_b, chunked: a thread owns L buckets, forms the running-sum
+//                 W_k and S_k, adds (k L) * S_k by a short double-and-add, then a tree sum.
+// Integer-multiply bound: 3 000 wide multiply-adds per bucket addition, 96 B of HBM per addition.
+#include <cub/device/device_radix_sort.cuh>
+#include "engine.cuh"
+
+namespace kzg {
+
+__device__ __forceinline__ void ld_affine_g(G1Affine& o, const G1Affine* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 r[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) r[i] = __ldg(q + i);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    o.x.v[4 * i] = r[i].x; o.x.v[4 * i + 1] = r[i].y; o.x.v[4 * i + 2] = r[i].z; o.x.v[4 * i + 3] = r[i].w;
+    o.y.v[4 * i] = r[3 + i].x; o.y.v[4 * i + 1] = r[3 + i].y; o.y.v[4 * i + 2] = r[3 + i].z; o.y.v[4 * i + 3] = r[3 + i].w;
+  }
+}
+
+__device__ __forceinline__ void ld_scalar(Fr& o, const uint8_t* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w;
+  o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+}
+
+__device__ __forceinline__ uint32_t window_at(const uint32_t* k, int bit, int c) {
+  int w = bit >> 5, sh = bit & 31;
+  if (w >= 8) return 0;
+  uint64_t lo = k[w];
+  if (w + 1 < 8) lo |= (uint64_t)k[w + 1] << 32;
+  return (uint32_t)(lo >> sh) & ((1u << c) - 1u);
+}
+
+// ---- 1. recode -------------------------------------------------------------------------------
+__global__ void k_recode(const uint8_t* __restrict__ scalars, uint64_t n, int c, int W, uint64_t n_stride,
+                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr k; ld_scalar(k, scalars + i * 32);
+  fr_canon_reduce(k);
+  const uint32_t half = 1u << (c - 1);
+  uint32_t carry = 0;
+  for (int j = 0; j < W; j++) {
+    uint32_t d = window_at(k.v, j * c, c) + carry;
+    bool negd = d > half;
+    if (negd) { d = (1u << c) - d; carry = 1; } else carry = 0;
+    keys[(size_t)j * n + i] = d ? d - 1 : half;            // `half` = discard bucket for zero digits
+    vals[(size_t)j * n + i] = (uint32_t)((uint64_t)j * n_stride + i) | (negd ? 0x80000000u : 0u);
+  }
+}
+
+// ---- 3. bucket bounds --------------------------------------------------------------------------
+__global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, uint64_t total, uint32_t nb,
+                                uint32_t* __restrict__ start) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  uint32_t k = keys[e];
+  uint32_t lo = e ? keys[e - 1] + 1 : 0;
+  for (uint32_t b = lo; b <= k; b++) start[b] = (uint32_t)e;
+  if (e == total - 1)
+    for (uint32_t b = k + 1; b <= nb; b++) start[b] = (uint32_t)total;
+}
+
+// ---- 4. accumulate -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_bucket_acc(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
+             const G1Affine* __restrict__ tab, uint32_t nbuckets, uint32_t heavy_cap,
+             G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  uint32_t s = start[b], e = start[b + 1];
+  if (e - s > heavy_cap) {
+    uint32_t slot = atomicAdd(heavy_count, 1u);
+    heavy_list[slot] = b;
+    return;
+  }
+  G1Xyzz acc; set_inf(acc);
+#pragma unroll 1
+  for (uint32_t k = s; k < e; k++) {
+    uint32_t v = __ldg(vals + k);
+    G1Affine p; ld_affine_g(p, tab + (v & 0x7FFFFFFFu));
+    madd(acc, p, (v >> 31) != 0);
+  }
+  buckets[b] = acc;
+}
+
+// block-per-heavy-bucket: strided partial sums + shared-memory tree
+__global__ void __launch_bounds__(128)
+k_bucket_heavy(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
+               const G1Affine* __restrict__ tab, G1Xyzz* __restrict__ buckets,
+               const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count) {
+  __shared__ G1Xyzz sh[128];
+  uint32_t nh = *heavy_count;
+  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+    uint32_t b = heavy_list[h];
+    uint32_t s = start[b], e = start[b + 1];
+    G1Xyzz acc; set_inf(acc);
+#pragma unroll 1
+    for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) {
+      uint32_t v = __ldg(vals + k);
+      G1Affine p; ld_affine_g(p, tab + (v & 0x7FFFFFFFu));
+      madd(acc, p, (v >> 31) != 0);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t st = 64; st >= 1; st >>= 1) {
+      if (threadIdx.x < st) { G1Xyzz o = sh[threadIdx.x + st]; add(acc, o); sh[threadIdx.x] = acc; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[b] = acc;
+    __syncthreads();
+  }
+}
+
+// ---- 5. reduce ---------------------------------------------------------------------------------
+__device__ __forceinline__ void small_mul(G1Xyzz& o, const G1Xyzz& p, uint32_t m) {
+  G1Xyzz acc; set_inf(acc);
+  if (m == 0 || is_inf(p)) { o = acc; return; }
+  for (int i = 31 - __clz(m); i >= 0; i--) {
+    dbl(acc);
+    if ((m >> i) & 1) add(acc, p);
+  }
+  o = acc;
+}
+
+// out[k] = sum_{l<L} (k L + l + 1) * B[k L + l]
+__global__ void __launch_bounds__(128)
+k_bucket_reduce(const G1Xyzz* __restrict__ buckets, uint32_t M, uint32_t L, G1Xyzz* __restrict__ out) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t chunks = (M + L - 1) / L;
+  if (k >= chunks) return;
+  G1Xyzz run, acc; set_inf(run); set_inf(acc);
+#pragma unroll 1
+  for (int l = (int)L - 1; l >= 0; l--) {
+    uint32_t idx = k * L + (uint32_t)l;
+    if (idx < M) { G1Xyzz b = buckets[idx]; add(run, b); }
+    add(acc, run);
+  }
+  G1Xyzz P; small_mul(P, run, k * L);
+  add(acc, P);
+  out[k] = acc;
+}
+
+// out[k] = sum of in[k L .. k L + L)
+__global__ void __launch_bounds__(128)
+k_sum_chunks(const G1Xyzz* __restrict__ in, uint64_t count, uint32_t L, G1Xyzz* __restrict__ out) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t chunks = (count + L - 1) / L;
+  if (k >= chunks) return;
+  G1Xyzz acc; set_inf(acc);
+#pragma unroll 1
+  for (uint32_t l = 0; l < L; l++) {
+    uint64_t idx = k * L + l;
+    if (idx < count) { G1Xyzz b = in[idx]; add(acc, b); }
+  }
+  out[k] = acc;
+}
+
+__global__ void k_set_inf(G1Xyzz* out, uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) { G1Xyzz p; set_inf(p); out[i] = p; }
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev) {
+  if (count == 0) {
+    k_set_inf<<<1, 32, 0, ctx->stream>>>(out_dev, 1);
+    KZG_LAUNCHED(ctx);
+    return KZG_OK;
+  }
+  const uint32_t L = 8;
+  void *a, *b;
+  uint64_t c1 = (count + L - 1) / L;
+  KZG_TRY(scratch_get(ctx, SCR_RED_A, (c1 + 1) * sizeof(G1Xyzz), &a));
+  KZG_TRY(scratch_get(ctx, SCR_RED_B, ((c1 + L - 1) / L + 1) * sizeof(G1Xyzz), &b));
+  const G1Xyzz* src = in_dev;
+  G1Xyzz* bufs[2] = {reinterpret_cast<G1Xyzz*>(a), reinterpret_cast<G1Xyzz*>(b)};
+  int which = 0;
+  while (true) {
+    uint64_t chunks = (count + L - 1) / L;
+    G1Xyzz* dst = chunks == 1 ? out_dev : bufs[which];
+    k_sum_chunks<<<blocks_for(chunks, 128), 128, 0, ctx->stream>>>(src, count, L, dst);
+    KZG_LAUNCHED(ctx);
+    if (chunks == 1) break;
+    src = dst; count = chunks; which ^= 1;
+  }
+  return KZG_OK;
+}
+
+int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
+                   G1Xyzz* result_dev) {
+  if (n == 0) {
+    k_set_inf<<<1, 32, 0, ctx->stream>>>(result_dev, 1);
+    KZG_LAUNCHED(ctx);
+    return KZG_OK;
+  }
+  if (!s->msm_tab) return fail(ctx, KZG_E_BAD_ARG, "msm table not prepared");
+  const int c = s->msm_c, W = s->msm_w;
+  const uint32_t half = 1u << (c - 1);
+  const uint64_t total = (uint64_t)W * n;
+  if ((uint64_t)W * s->n >= (1ull << 31) || total >= (1ull << 32))
+    return fail(ctx, KZG_E_BAD_ARG, "msm too large for 31-bit table indices");
+
+  void *ka, *kb, *va, *vb, *st, *bk, *hv, *red;
+  KZG_TRY(scratch_get(ctx, SCR_KEYS_A, total * 4, &ka));
+  KZG_TRY(scratch_get(ctx, SCR_KEYS_B, total * 4, &kb));
+  KZG_TRY(scratch_get(ctx, SCR_VALS_A, total * 4, &va));
+  KZG_TRY(scratch_get(ctx, SCR_VALS_B, total * 4, &vb));
+  KZG_TRY(scratch_get(ctx, SCR_BUCKET_START, ((size_t)half + 3) * 4, &st));
+  KZG_TRY(scratch_get(ctx, SCR_BUCKETS, (size_t)half * sizeof(G1Xyzz), &bk));
+  const uint32_t heavy_cap = (uint32_t)ctx->opt_heavy_cap;
+  size_t heavy_max = total / heavy_cap + 2;
+  KZG_TRY(scratch_get(ctx, SCR_HEAVY, (heavy_max + 1) * 4, &hv));
+  uint32_t* heavy_count = reinterpret_cast<uint32_t*>(hv);
+  uint32_t* heavy_list = heavy_count + 1;
+
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  k_recode<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(scalars_dev, n, c, W, s->n,
+                                                        reinterpret_cast<uint32_t*>(ka), reinterpret_cast<uint32_t*>(va));
+  KZG_LAUNCHED(ctx);
+
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, reinterpret_cast<uint32_t*>(ka), reinterpret_cast<uint32_t*>(kb),
+                                  reinterpret_cast<uint32_t*>(va), reinterpret_cast<uint32_t*>(vb), (uint64_t)total, 0, c,
+                                  ctx->stream);
+  void* tmp;
+  KZG_TRY(scratch_get(ctx, SCR_SORT_TMP, tmp_bytes + 16, &tmp));
+  KZG_CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, reinterpret_cast<uint32_t*>(ka),
+                                                   reinterpret_cast<uint32_t*>(kb), reinterpret_cast<uint32_t*>(va),
+                                                   reinterpret_cast<uint32_t*>(vb), (uint64_t)total, 0, c, ctx->stream));
+  ctx->launches += 4;  // cub onesweep: histogram + scan + one pass per 8 key bits (approximate)
+
+  k_bucket_bounds<<<blocks_for(total, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(kb), total, half,
+                                                                   reinterpret_cast<uint32_t*>(st));
+  KZG_LAUNCHED(ctx);
+  KZG_CUDA_OK(ctx, cudaMemsetAsync(heavy_count, 0, 4, ctx->stream));
+
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  k_bucket_acc<<<blocks_for(half, 128), 128, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(st),
+                                                               reinterpret_cast<uint32_t*>(vb), s->msm_tab, half, heavy_cap,
+                                                               reinterpret_cast<G1Xyzz*>(bk), heavy_list, heavy_count);
+  KZG_LAUNCHED(ctx);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  k_bucket_heavy<<<32, 128, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb),
+                                              s->msm_tab, reinterpret_cast<G1Xyzz*>(bk), heavy_list, heavy_count);
+  KZG_LAUNCHED(ctx);
+
+  uint32_t L = (uint32_t)ctx->opt_reduce_chunk;
+  if (L < 2) L = 2;
+  uint32_t chunks = (half + L - 1) / L;
+  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, (size_t)chunks * sizeof(G1Xyzz), &red));
+  k_bucket_reduce<<<blocks_for(chunks, 128), 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(bk), half, L,
+                                                                    reinterpret_cast<G1Xyzz*>(red));
+  KZG_LAUNCHED(ctx);
+  KZG_TRY(sum_points(ctx, reinterpret_cast<G1Xyzz*>(red), chunks, result_dev));
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  return KZG_OK;
+}
+
+}  // namespace kzg

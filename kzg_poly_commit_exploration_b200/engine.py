@@ -1,0 +1,187 @@
+"""Thin object layer over the C ABI: Context (one CUDA device) and Setup (device-resident bases)."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _native as N
+
+
+def _ptr(x):
+    """bytes / bytearray / ctypes array / int (device or pinned-host address) -> void*"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(x)), C.c_void_p)
+    return C.cast(x, C.c_void_p)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        st = N.lib().kzg_ctx_create(C.byref(self._h), device)
+        if st != N.KZG_OK:
+            raise N.KzgNativeError(st, f"kzg_ctx_create(device={device}) failed: no usable CUDA device (no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            N.lib().kzg_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st: int):
+        if st != N.KZG_OK:
+            msg = N.lib().kzg_last_error(self._h).decode(errors="replace")
+            raise N.KzgNativeError(st, msg or N.lib().kzg_status_string(st).decode())
+
+    # ---- misc -------------------------------------------------------------------------
+    def sync(self):
+        self.check(N.lib().kzg_ctx_sync(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(N.lib().kzg_ctx_launch_count(self._h))
+
+    def last_kernel_ms(self, which: int = 0) -> float:
+        return float(N.lib().kzg_ctx_last_kernel_ms(self._h, which))
+
+    def set_option(self, name: str, value: int):
+        self.check(N.lib().kzg_ctx_set_option(self._h, name.encode(), value))
+
+    def probe_imad_peak(self) -> float:
+        v = C.c_double()
+        self.check(N.lib().kzg_probe_imad_peak(self._h, C.byref(v)))
+        return v.value
+
+    def probe_fq_mul(self) -> float:
+        v = C.c_double()
+        self.check(N.lib().kzg_probe_fq_mul(self._h, C.byref(v)))
+        return v.value
+
+    def selftest_fq_mul(self, a: bytes, b: bytes) -> bytes:
+        n = len(a) // 48
+        o = N.out(n * 48)
+        self.check(N.lib().kzg_selftest_fq_mul(self._h, _ptr(a), _ptr(b), n, o))
+        return bytes(o)
+
+    # ---- setup ------------------------------------------------------------------------
+    def setup_generate(self, secret_be: bytes, n: int, first: int = 0) -> "Setup":
+        assert len(secret_be) == 32
+        h = C.c_void_p()
+        self.check(N.lib().kzg_setup_generate(self._h, _ptr(secret_be), first, n, C.byref(h)))
+        return Setup(self, h)
+
+    def setup_import_g1(self, g1_c48: bytes) -> "Setup":
+        if len(g1_c48) % 48:
+            raise N.KzgNativeError(5, f"Invalid length, expected a multiple of 48, got {len(g1_c48)}")
+        h = C.c_void_p()
+        self.check(N.lib().kzg_setup_import_g1(self._h, _ptr(g1_c48), len(g1_c48) // 48, C.byref(h)))
+        return Setup(self, h)
+
+    # ---- bulk operations (host buffers) -------------------------------------------------
+    def commit(self, setup: "Setup", coeffs_le32, n: int | None = None) -> bytes:
+        n = len(coeffs_le32) // 32 if n is None else n
+        o = N.out(48)
+        self.check(N.lib().kzg_commit(self._h, setup._h, _ptr(coeffs_le32), n, o))
+        return bytes(o)
+
+    def msm_g1(self, setup: "Setup", scalars_le32, n: int | None = None) -> bytes:
+        n = len(scalars_le32) // 32 if n is None else n
+        o = N.out(48)
+        self.check(N.lib().kzg_msm_g1(self._h, setup._h, _ptr(scalars_le32), n, o))
+        return bytes(o)
+
+    def evaluate(self, coeffs_le32, z_le: bytes, n: int | None = None) -> bytes:
+        n = len(coeffs_le32) // 32 if n is None else n
+        o = N.out(32)
+        self.check(N.lib().kzg_evaluate(self._h, _ptr(coeffs_le32), n, _ptr(z_le), o))
+        return bytes(o)
+
+    def quotient(self, coeffs_le32, z_le: bytes, y_le: bytes | None = None, n: int | None = None) -> bytes:
+        n = len(coeffs_le32) // 32 if n is None else n
+        o = N.out(max(n, 1) * 32)
+        ql = C.c_uint64()
+        self.check(N.lib().kzg_quotient(self._h, _ptr(coeffs_le32), n, _ptr(z_le), _ptr(y_le), o, C.byref(ql)))
+        return bytes(o)[: ql.value * 32]
+
+    def open(self, setup: "Setup", coeffs_le32, z_le: bytes, y_expected_le: bytes | None = None, n: int | None = None):
+        n = len(coeffs_le32) // 32 if n is None else n
+        y, pr = N.out(32), N.out(48)
+        self.check(N.lib().kzg_open(self._h, setup._h, _ptr(coeffs_le32), n, _ptr(z_le), _ptr(y_expected_le), y, pr))
+        return bytes(y), bytes(pr)
+
+    def commit_batch(self, setup: "Setup", coeffs_le32, blobs: int, n: int, out=None) -> bytes:
+        o = N.out(blobs * 48) if out is None else out
+        self.check(N.lib().kzg_commit_batch(self._h, setup._h, _ptr(coeffs_le32), blobs, n, _ptr(o)))
+        return bytes(o) if out is None else out
+
+    def open_batch(self, setup: "Setup", coeffs_le32, blobs: int, n: int, z_le32, y_out=None, proofs_out=None):
+        y = N.out(blobs * 32) if y_out is None else y_out
+        pr = N.out(blobs * 48) if proofs_out is None else proofs_out
+        self.check(N.lib().kzg_open_batch(self._h, setup._h, _ptr(coeffs_le32), blobs, n, _ptr(z_le32), _ptr(y), _ptr(pr)))
+        return (bytes(y), bytes(pr)) if y_out is None else (y, pr)
+
+    # ---- device-resident variants (addresses as ints, e.g. torch.Tensor.data_ptr()) ---------
+    def msm_g1_dev(self, setup: "Setup", scalars_dev: int, n: int) -> bytes:
+        o = N.out(48)
+        self.check(N.lib().kzg_msm_g1_dev(self._h, setup._h, _ptr(scalars_dev), n, o))
+        return bytes(o)
+
+    def msm_g1_partial_dev(self, setup: "Setup", scalars_dev: int, n: int, partial_dev: int):
+        self.check(N.lib().kzg_msm_g1_partial_dev(self._h, setup._h, _ptr(scalars_dev), n, _ptr(partial_dev)))
+
+    def g1_combine_dev(self, partials_dev: int, count: int) -> bytes:
+        o = N.out(48)
+        self.check(N.lib().kzg_g1_combine_dev(self._h, _ptr(partials_dev), count, o))
+        return bytes(o)
+
+    def commit_batch_dev(self, setup: "Setup", coeffs_dev: int, blobs: int, n: int, out_dev: int):
+        self.check(N.lib().kzg_commit_batch_dev(self._h, setup._h, _ptr(coeffs_dev), blobs, n, _ptr(out_dev)))
+
+    def open_batch_dev(self, setup: "Setup", coeffs_dev: int, blobs: int, n: int, z_dev: int, y_dev: int, proofs_dev: int):
+        self.check(N.lib().kzg_open_batch_dev(self._h, setup._h, _ptr(coeffs_dev), blobs, n, _ptr(z_dev), _ptr(y_dev), _ptr(proofs_dev)))
+
+    def evaluate_dev(self, coeffs_dev: int, n: int, z_le: bytes) -> bytes:
+        o = N.out(32)
+        self.check(N.lib().kzg_evaluate_dev(self._h, _ptr(coeffs_dev), n, _ptr(z_le), o))
+        return bytes(o)
+
+
+class Setup:
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+
+    def __len__(self):
+        return int(N.lib().kzg_setup_len(self._h))
+
+    def export_g1(self, first: int = 0, count: int | None = None) -> bytes:
+        count = len(self) - first if count is None else count
+        o = N.out(max(count, 1) * 48)
+        self.ctx.check(N.lib().kzg_setup_export_g1(self.ctx._h, self._h, first, count, o))
+        return bytes(o)[: count * 48]
+
+    def prepare_msm(self, window_bits: int = 0):
+        self.ctx.check(N.lib().kzg_setup_prepare_msm(self.ctx._h, self._h, window_bits))
+
+    def prepare_fixed(self, n_points: int, window_bits: int = 0):
+        self.ctx.check(N.lib().kzg_setup_prepare_fixed(self.ctx._h, self._h, n_points, window_bits))
+
+    def close(self):
+        if self._h:
+            N.lib().kzg_setup_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.close()
+        except Exception:
+            pass

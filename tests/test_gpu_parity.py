@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Sizes the oracle finishes in seconds use its restatement of the reference loops; larger sizes
+use the known-secret identities: every test setup comes from a seeded secret s, so
+commit(p) = [p(s)]G1 and proof(p,z) = [(p(s)-p(z))/(s-z)]G1 are one scalar multiplication."""
+import random
+
+import pytest
+
+import kzg_oracle as O
+import util
+
+pytestmark = pytest.mark.gpu
+
+SECRET = O.BENCH_SECRET_BE
+S = O.fr_from_be_bytes(SECRET)
+
+
+@pytest.fixture(scope="module")
+def setup8k(ctx):
+    s = ctx.setup_generate(SECRET, 8192)
+    yield s
+    s.close()
+
+
+def g1c(k):
+    return O.g1_compress(O.g1_mul(O.G1, k % O.R))
+
+
+# ---- field ---------------------------------------------------------------------------------
+def test_fq_field_kernel(ctx):
+    rnd = random.Random(11)
+    vals = [0, 1, O.Q - 1, O.Q - 2, (O.Q - 1) // 2, 2**380] + [rnd.randrange(O.Q) for _ in range(500)]
+    a = vals
+    b = [vals[(7 * i + 3) % len(vals)] for i in range(len(vals))]
+    ab = b"".join(x.to_bytes(48, "little") for x in a)
+    bb = b"".join(x.to_bytes(48, "little") for x in b)
+    got = ctx.selftest_fq_mul(ab, bb)
+    for i, (x, y) in enumerate(zip(a, b)):
+        exp = (x * y + x * x * y - x) % O.Q
+        assert int.from_bytes(got[48 * i: 48 * i + 48], "little") == exp, i
+
+
+# ---- setup -----------------------------------------------------------------------------------
+def test_setup_kat_and_known_secret(ctx, setup8k):
+    assert len(setup8k) == 8192
+    pts = setup8k.export_g1(0, 3)
+    assert pts[:48].hex() == "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    assert pts[48:96].hex() == "95fde78acd5f6886ddaf5d0056610167c513d09c1c0efabbc7cdcc69beea113779c4a81e2d24daafc5387dbf6ac5fe48"
+    assert pts[96:144].hex() == "975c1540dc41410552b33b489013bdf4e026d78d25a9a7b2075225b29efeff0046ddb2e58f4a4b0c21c825f20bae1181"
+    allpts = setup8k.export_g1()
+    for i in [3, 31, 32, 33, 63, 64, 1000, 4095, 4096, 8191]:
+        assert allpts[48 * i: 48 * i + 48] == g1c(pow(S, i, O.R)), i
+
+
+def test_setup_shard_offset_and_secret_reduction(ctx):
+    # secret >= r is reduced (src/lib.rs:44-46 exercises this); `first` shards by index range
+    secret = bytes([0xFF] * 32)
+    s = O.fr_from_be_bytes(secret)
+    st = ctx.setup_generate(secret, 70, first=1000)
+    pts = st.export_g1()
+    for i in [0, 1, 31, 32, 69]:
+        assert pts[48 * i: 48 * i + 48] == g1c(pow(s, 1000 + i, O.R)), i
+    st.close()
+
+
+@pytest.mark.parametrize("secret_int", [0, 1])
+def test_setup_degenerate_secrets(ctx, secret_int):
+    # s = 0: item 0 is the generator, every later item is infinity (SURVEY §8c edge 7); s = 1: all G
+    st = ctx.setup_generate(secret_int.to_bytes(32, "big"), 5)
+    pts = st.export_g1()
+    assert pts[:48] == O.g1_compress(O.G1)
+    for i in range(1, 5):
+        assert pts[48 * i: 48 * i + 48] == (O.g1_compress(None) if secret_int == 0 else O.g1_compress(O.G1))
+    # commits over degenerate bases exercise the infinity / doubling paths of the bucket adds
+    coeffs = util.scalar_stream_bytes(7, 5)
+    ints = util.to_ints(coeffs)
+    exp = ints[0] if secret_int == 0 else sum(ints)
+    assert ctx.commit(st, coeffs) == g1c(exp)
+    st.close()
+
+
+def test_setup_import_export_roundtrip(ctx, setup8k, native):
+    pts = setup8k.export_g1(0, 100) + O.g1_compress(None) + O.g1_compress(O.g1_neg(O.G1))
+    st = ctx.setup_import_g1(pts)
+    assert st.export_g1() == pts
+    coeffs = util.scalar_stream_bytes(3, 100)
+    assert ctx.commit(st, coeffs) == ctx.commit(setup8k, coeffs)
+    st.close()
+    bad = bytearray(pts)
+    bad[48 * 5 + 47] ^= 1
+    # flipping a bit of x lands off-curve about half the time; find one that does
+    for flip in range(1, 64):
+        bad = bytearray(pts)
+        bad[48 * 5 + 47] ^= flip
+        try:
+            O.g1_uncompress(bytes(bad[48 * 5: 48 * 6]))
+        except O.KzgError:
+            break
+    with pytest.raises(native.KzgNativeError) as ei:
+        ctx.setup_import_g1(bytes(bad))
+    assert ei.value.kind == "BAD_POINT"
+    with pytest.raises(native.KzgNativeError) as ei:
+        ctx.setup_import_g1(b"\x00" * 48)  # compression bit missing
+    assert ei.value.kind == "BAD_POINT"
+
+
+# ---- evaluate / quotient -----------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 8, 9, 511, 4095, 4096, 4097, 8193, 20000])
+def test_evaluate_and_quotient(ctx, n):
+    rnd = random.Random(n)
+    ints = [rnd.randrange(1 << 256) for _ in range(n)]  # includes values >= r: reduced like from_le_bytes
+    if n > 3:
+        ints[1] = 0
+        ints[2] = O.R  # == 0 mod r
+        ints[n - 1] = rnd.randrange(1, O.R)
+    z = rnd.randrange(1 << 256)
+    coeffs = util.from_ints(ints)
+    red = [v % O.R for v in ints]
+    y = ctx.evaluate(coeffs, util.le(z))
+    assert int.from_bytes(y, "little") == O.horner(red, z % O.R)
+    if n >= 2:
+        q_exp, y_exp = O.quotient(red, z % O.R)
+        q = ctx.quotient(coeffs, util.le(z))
+        assert util.to_ints(q) == q_exp
+        q2 = ctx.quotient(coeffs, util.le(z), util.le(y_exp))
+        assert q2 == q
+
+
+def test_quotient_error_cases(ctx, native):
+    # divide_by_root errors (src/polynomial.rs:159-166, 188-192) and the two zero-polynomial forms
+    z = util.le(5)
+    p = util.from_ints([3, 1, 4, 1, 5])
+    y = O.horner([3, 1, 4, 1, 5], 5)
+    with pytest.raises(native.KzgNativeError) as ei:
+        ctx.quotient(p, z, util.le(y + 1))
+    assert ei.value.kind == "REMAINDER_NONZERO"
+    const = util.from_ints([9, 0, 0])  # trims to the constant 9
+    assert ctx.quotient(const, z, util.le(9)) == b""
+    with pytest.raises(native.KzgNativeError) as ei:
+        ctx.quotient(const, z, util.le(8))
+    assert ei.value.kind == "CONSTANT_POLY"
+    assert ctx.quotient(util.from_ints([0, 0]), z, util.le(0)) == b""
+    assert ctx.quotient(b"", z, util.le(0)) == b""
+    # degree one: the division loop body never runs, quotient = [c1] (SURVEY §8c edge 6)
+    assert util.to_ints(ctx.quotient(util.from_ints([11, 15]), util.le(25))) == [15]
+
+
+# ---- commit / open: reference bench inputs (known-answer vectors) --------------------------------
+KAT = {
+    1: ("add892451b1c924699eaadfa1566680ac35623081bd4c71db9aa61019f80283e7ab2f173a9d68b11d9defeb998b988bd",
+        "8201000000000000000000000000000000000000000000000000000000000000",
+        "8d9e19b3f4c7c233a6112e5397309f9812a4f61f754f11dd3dcb8b07d55a7b1dfea65f19a1488a14fef9a41495083582"),
+    100: ("ab62ff5bdabc092b554b00b478180ac525b35286b27cda3cfde216444babf0e0618b84fa4f66bb293a69f57bbbf8afd5",
+          "2c3ce3804bf01f3238eee31be59f0569db9d5431e9d9f7cdc776a96bb7f45473",
+          "b7ea466c24ba3846fc304900816ba39db71ec361a1b6d48defa645be983bc88eb012df27afbbdbf09805a9e595cfd585"),
+    1000: ("86e2e5fe20957b704891436d5a854467c0ef2b60cb9c1c45c021959ebeccb6298ca33bca3dc8f6239571ad8ac3b62cde",
+           "2fd5e9231009e440887b7c824aea88cd4238b23dd444bc489f5ae47553971a0c",
+           "a9c0d6b86411efe1cc49cf958c524e57d2d9edc1a67617628a4e5c71760c6725175216e8db6d12b3fb1527fbe644f6b4"),
+    1023: ("aa76be9eb3642542c1be5d4b32793ea043b60dd75e19c5d22fefb6db7f7b3dbdd094b54c1a4124156af4d675235fd673",
+           "11ef23ab6ee756b8d2ba8da407a71c748559e0f91d18d1c661c8b12a40d23433",
+           "80eb18a680b920a6187c3d76c36ab4f592e269342928691d3a25aa3c996dfcbca7d28a741d71db5066b1ba727402c8ff"),
+}
+
+
+@pytest.mark.parametrize("degree", [1, 100, 500, 1000, 1023, 2500])
+def test_commit_open_bench_inputs(ctx, setup8k, degree):
+    co = O.bench_polynomial(degree)
+    z = O.bench_input_point(degree)
+    coeffs = util.from_ints(co)
+    c = ctx.commit(setup8k, coeffs)
+    y, proof = ctx.open(setup8k, coeffs, util.le(z))
+    assert c == O.g1_compress(O.commit_known_secret(co, S))
+    assert int.from_bytes(y, "little") == O.horner(co, z)
+    assert proof == O.g1_compress(O.proof_known_secret(co, S, z))
+    if degree in KAT:
+        assert (c.hex(), y.hex(), proof.hex()) == KAT[degree]
+    # generate_proof with the evaluation's own result is accepted, a wrong one is rejected
+    y2, proof2 = ctx.open(setup8k, coeffs, util.le(z), y)
+    assert (y2, proof2) == (y, proof)
+
+
+def test_open_errors_and_degree_check(ctx, setup8k, native):
+    small = ctx.setup_generate(SECRET, 4)
+    ok = util.from_ints([1, 2, 3, 4])
+    assert ctx.commit(small, ok) == O.g1_compress(O.commit_known_secret([1, 2, 3, 4], S))
+    # the TRIMMED degree is what is checked against the setup (src/polynomial.rs:201-205)
+    assert ctx.commit(small, util.from_ints([1, 2, 3, 4, 0, O.R])) == ctx.commit(small, ok)
+    with pytest.raises(native.KzgNativeError) as ei:
+        ctx.commit(small, util.from_ints([1, 2, 3, 4, 5]))
+    assert ei.value.kind == "DEGREE_TOO_HIGH"
+    # zero polynomial -> infinity, c0 00..00
+    assert ctx.commit(small, util.from_ints([0, 0, 0])) == O.g1_compress(None)
+    assert ctx.commit(small, b"") == O.g1_compress(None)
+    with pytest.raises(native.KzgNativeError) as ei:
+        ctx.open(small, ok, util.le(7), util.le(123))
+    assert ei.value.kind == "REMAINDER_NONZERO"
+    # constant polynomial: right result -> proof = infinity; wrong -> "Unable to divide a constant polynomial"
+    y, pr = ctx.open(small, util.from_ints([42]), util.le(7), util.le(42))
+    assert int.from_bytes(y, "little") == 42 and pr == O.g1_compress(None)
+    with pytest.raises(native.KzgNativeError) as ei:
+        ctx.open(small, util.from_ints([42]), util.le(7), util.le(41))
+    assert ei.value.kind == "CONSTANT_POLY"
+    small.close()
+
+
+def test_commit_matches_reference_loop(ctx):
+    """Small case against the oracle's restatement of the naive loop (src/polynomial.rs:207-212),
+    with i128-range coefficients as the reference's own tests use (src/lib.rs:35-41)."""
+    rnd = random.Random(99)
+    secret = rnd.randbytes(32)
+    setup = O.setup_generate(secret, 12)
+    st = ctx.setup_generate(secret, 12)
+    assert st.export_g1() == b"".join(O.g1_compress(a.g1) for a in setup)
+    vals = [rnd.randrange(-(1 << 127), 1 << 127) for _ in range(12)]
+    poly = O.Polynomial.try_from_i128(vals)
+    coeffs = util.from_ints(poly.coefficients)
+    z = O.fr_from_i128(rnd.randrange(-(1 << 127), 1 << 127))
+    ev = poly.evaluate(z)
+    c = ctx.commit(st, coeffs)
+    y, pr = ctx.open(st, coeffs, util.le(z))
+    assert c == O.g1_compress(poly.commit(setup))
+    assert y == O.fr_to_le_bytes(ev.result)
+    assert pr == O.g1_compress(ev.generate_proof(poly, setup))
+    # the reference's acceptance test: pairing check on the GPU outputs (src/lib.rs:16-33)
+    assert ev.verify_proof(O.g1_uncompress(pr), O.g1_uncompress(c), setup)
+    st.close()
+
+
+# ---- adversarial scalar sets (bucket collisions, heavy buckets, cancellations) ----------------------
+@pytest.mark.parametrize("kind", ["zeros", "ones", "equal", "rminus1", "small", "alternating"])
+def test_commit_adversarial_scalars(ctx, setup8k, kind):
+    n = 3000
+    rnd = random.Random(5)
+    if kind == "zeros":
+        ints = [0] * n
+    elif kind == "ones":
+        ints = [1] * n
+    elif kind == "equal":
+        ints = [rnd.randrange(O.R)] * n
+    elif kind == "rminus1":
+        ints = [O.R - 1] * n
+    elif kind == "small":
+        ints = [rnd.randrange(4) for _ in range(n)]
+    else:
+        v = rnd.randrange(O.R)
+        ints = [v if i % 2 == 0 else O.R - v for i in range(n)]
+    got = ctx.msm_g1(setup8k, util.from_ints(ints))
+    assert got == O.g1_compress(O.commit_known_secret(ints, S))
+
+
+@pytest.mark.parametrize("c", [4, 7, 11, 13, 16])
+def test_msm_window_sizes(ctx, c):
+    st = ctx.setup_generate(SECRET, 2000)
+    st.prepare_msm(c)
+    scal = util.scalar_stream_bytes(c, 2000)
+    assert ctx.msm_g1(st, scal) == O.g1_compress(O.commit_known_secret(util.to_ints(scal), S))
+    # heavy-bucket path: force it with a tiny cap
+    ctx.set_option("heavy_cap", 3)
+    try:
+        assert ctx.msm_g1(st, scal) == O.g1_compress(O.commit_known_secret(util.to_ints(scal), S))
+    finally:
+        ctx.set_option("heavy_cap", 1024)
+    st.close()
+
+
+# ---- fixed-base batch path (blob configuration) ------------------------------------------------------
+@pytest.mark.parametrize("c", [4, 8])
+def test_blob_batch_small(ctx, c):
+    n, blobs = 256, 7
+    st = ctx.setup_generate(SECRET, n)
+    st.prepare_fixed(n, c)
+    coeffs = util.scalar_stream_bytes(0xC4, blobs * n)
+    zs = util.scalar_stream_bytes(0xC4F, blobs)
+    commits = ctx.commit_batch(st, coeffs, blobs, n)
+    ys, proofs = ctx.open_batch(st, coeffs, blobs, n, zs)
+    for b in range(blobs):
+        co = util.to_ints(coeffs[b * n * 32: (b + 1) * n * 32])
+        z = int.from_bytes(zs[32 * b: 32 * b + 32], "little")
+        assert commits[48 * b: 48 * b + 48] == O.g1_compress(O.commit_known_secret(co, S)), b
+        assert int.from_bytes(ys[32 * b: 32 * b + 32], "little") == O.horner(co, z), b
+        assert proofs[48 * b: 48 * b + 48] == O.g1_compress(O.proof_known_secret(co, S, z)), b
+    # single commits below the table size take the same fixed-base path
+    co = util.to_ints(coeffs[: 100 * 32])
+    assert ctx.commit(st, coeffs[: 100 * 32]) == O.g1_compress(O.commit_known_secret(co, S))
+    st.close()
+
+
+def test_blob_batch_without_fixed_table_uses_bucket_msm(ctx, setup8k):
+    n, blobs = 300, 3
+    coeffs = util.scalar_stream_bytes(21, blobs * n)
+    commits = ctx.commit_batch(setup8k, coeffs, blobs, n)
+    for b in range(blobs):
+        co = util.to_ints(coeffs[b * n * 32: (b + 1) * n * 32])
+        assert commits[48 * b: 48 * b + 48] == O.g1_compress(O.commit_known_secret(co, S)), b
+
+
+# ---- sharded MSM: partial sums combined on the device --------------------------------------------------
+def test_sharded_partials_combine(ctx):
+    import torch
+
+    n, shards = 6000, 3
+    scal = util.scalar_stream_bytes(0xC3, n)
+    full = O.g1_compress(O.commit_known_secret(util.to_ints(scal), S))
+    dev = torch.device("cuda:0")
+    partials = torch.zeros(shards * 192, dtype=torch.uint8, device=dev)
+    per = n // shards
+    keep = []
+    for g in range(shards):
+        st = ctx.setup_generate(SECRET, per, first=g * per)       # rank g owns bases [g*per, (g+1)*per)
+        sc = torch.frombuffer(bytearray(scal[g * per * 32: (g + 1) * per * 32]), dtype=torch.uint8).to(dev)
+        ctx.msm_g1_partial_dev(st, sc.data_ptr(), per, partials.data_ptr() + 192 * g)
+        keep.append((st, sc))
+    ctx.sync()
+    assert ctx.g1_combine_dev(partials.data_ptr(), shards) == full
+    for st, _ in keep:
+        st.close()
+
+
+# ---- BASELINE config C2: degree 2^16 ------------------------------------------------------------------
+def test_config_c2_degree_65536(ctx):
+    n = 65537
+    st = ctx.setup_generate(SECRET, n)
+    coeffs = util.scalar_stream_bytes(0xC2, n)
+    z = O.scalar_stream(0xC2F, 0)
+    co = util.to_ints(coeffs)
+    assert st.export_g1(n - 1, 1) == g1c(pow(S, n - 1, O.R))
+    c = ctx.commit(st, coeffs)
+    y, pr = ctx.open(st, coeffs, util.le(z))
+    assert c == O.g1_compress(O.commit_known_secret(co, S))
+    assert int.from_bytes(y, "little") == O.horner(co, z)
+    assert pr == O.g1_compress(O.proof_known_secret(co, S, z))
+    st.close()
