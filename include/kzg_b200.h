@@ -61,6 +61,9 @@ uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx);
 /* device time of the last bulk call's dominant kernel(s) in ms, measured with CUDA events on
  * the ctx stream: which = 0 bucket accumulate / fixed-base accumulate, 1 whole call */
 float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which);
+/* CUDA-event stopwatch on the ctx stream (bench.py times its K-step region with it) */
+int32_t kzg_ctx_timer_start(kzg_ctx* ctx);
+int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms);
 /* tuning: window bits for the bucket MSM (0 = auto) and for the fixed-base batch tables */
 int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value);
 

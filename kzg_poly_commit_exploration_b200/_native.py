@@ -29,6 +29,8 @@ SIGNATURES = {
     "kzg_ctx_sync": (_i32, [_vp]),
     "kzg_ctx_launch_count": (_u64, [_vp]),
     "kzg_ctx_last_kernel_ms": (C.c_float, [_vp, _i32]),
+    "kzg_ctx_timer_start": (_i32, [_vp]),
+    "kzg_ctx_timer_stop": (_i32, [_vp, C.POINTER(C.c_float)]),
     "kzg_ctx_set_option": (_i32, [_vp, C.c_char_p, C.c_int64]),
     "kzg_setup_generate": (_i32, [_vp, _vp, _u64, _u64, C.POINTER(_vp)]),
     "kzg_setup_import_g1": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),

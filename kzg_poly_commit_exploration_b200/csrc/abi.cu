@@ -113,6 +113,7 @@ int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
   for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
   for (int i = 0; i < 4; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+  for (int i = 0; i < 2; i++) { cudaEventCreate(&ctx->ev_t[i]); cudaEventRecord(ctx->ev_t[i], ctx->stream); }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   cudaStreamSynchronize(ctx->stream);
@@ -128,6 +129,7 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->gtable) cudaFree(ctx->gtable);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; i++) if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -138,6 +140,20 @@ int32_t kzg_ctx_sync(kzg_ctx* ctx) {
   DeviceGuard g(ctx->device);
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   update_timers(ctx);
+  return KZG_OK;
+}
+
+int32_t kzg_ctx_timer_start(kzg_ctx* ctx) {
+  DeviceGuard g(ctx->device);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_t[0], ctx->stream));
+  return KZG_OK;
+}
+
+int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
+  DeviceGuard g(ctx->device);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_t[1], ctx->stream));
+  KZG_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_t[1]));
+  KZG_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev_t[0], ctx->ev_t[1]));
   return KZG_OK;
 }
 

@@ -28,6 +28,7 @@ struct kzg_ctx {
   uint64_t launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[2] = {0.f, 0.f};
+  cudaEvent_t ev_t[2] = {nullptr, nullptr};
   void* scratch[kzg::SCR_COUNT] = {};
   size_t scratch_cap[kzg::SCR_COUNT] = {};
   void* pinned = nullptr;

@@ -52,6 +52,14 @@ class Context:
     def last_kernel_ms(self, which: int = 0) -> float:
         return float(N.lib().kzg_ctx_last_kernel_ms(self._h, which))
 
+    def timer_start(self):
+        self.check(N.lib().kzg_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self.check(N.lib().kzg_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def set_option(self, name: str, value: int):
         self.check(N.lib().kzg_ctx_set_option(self._h, name.encode(), value))
 
