@@ -15,7 +15,7 @@ enum ScratchSlot {
   SCR_KEYS_A, SCR_KEYS_B, SCR_VALS_A, SCR_VALS_B, SCR_SORT_TMP,
   SCR_BUCKET_START, SCR_BUCKETS, SCR_RED_A, SCR_RED_B, SCR_HEAVY,
   SCR_XYZZ_TMP, SCR_PREFIX, SCR_QUOT, SCR_SEG, SCR_OUT, SCR_MISC, SCR_FR_A, SCR_FR_B,
-  SCR_BATCH_PTS, SCR_BATCH_AFF,
+  SCR_BATCH_PTS, SCR_BATCH_AFF, SCR_PARTIALS, SCR_HEAVY_PARTS,
   SCR_COUNT
 };
 
@@ -38,6 +38,7 @@ struct kzg_ctx {
   int opt_fixed_window = 0;            // 0 = auto
   int opt_reduce_chunk = 16;
   int opt_heavy_cap = 1024;
+  int opt_acc_split = -1;              // log2(threads per bucket), -1 = auto
   int sm_count = 148;
 };
 

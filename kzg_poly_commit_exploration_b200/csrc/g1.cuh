@@ -95,12 +95,12 @@ KZG_HD void madd(G1Xyzz& a, const Fq& px, const Fq& py) {
 
 KZG_HD void madd(G1Xyzz& a, const G1Affine& p, bool negate) {
   if (is_inf(p)) return;
-  if (negate) {
-    Fq ny; neg(ny, p.y);
-    madd(a, p.x, ny);
-  } else {
-    madd(a, p.x, p.y);
-  }
+  // branch-free conditional negation: both signs must run the SAME madd instructions, otherwise a warp
+  // splits into a "+" half and a "-" half that execute two inlined copies of the addition
+  Fq y; neg(y, p.y);
+#pragma unroll
+  for (int i = 0; i < 12; i++) y.v[i] = negate ? y.v[i] : p.y.v[i];
+  madd(a, p.x, y);
 }
 
 // acc += b.  12M + 2S.
@@ -143,7 +143,7 @@ KZG_HD void to_affine_with_inv(G1Affine& o, const G1Xyzz& a, const Fq& zzz_inv) 
 }
 KZG_HD void to_affine(G1Affine& o, const G1Xyzz& a) {
   if (is_inf(a)) { set_inf(o); return; }
-  Fq w; inv(w, a.zzz);
+  Fq w; inv_gcd(w, a.zzz);
   to_affine_with_inv(o, a, w);
 }
 

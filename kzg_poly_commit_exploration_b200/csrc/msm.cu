@@ -78,41 +78,68 @@ __global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, uint64_t tota
 }
 
 // ---- 4. accumulate -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_bucket_acc(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
-             const G1Affine* __restrict__ tab, uint32_t nbuckets, uint32_t heavy_cap,
-             G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets) return;
-  uint32_t s = start[b], e = start[b + 1];
-  if (e - s > heavy_cap) {
-    uint32_t slot = atomicAdd(heavy_count, 1u);
-    heavy_list[slot] = b;
-    return;
-  }
-  G1Xyzz acc; set_inf(acc);
-#pragma unroll 1
-  for (uint32_t k = s; k < e; k++) {
-    uint32_t v = __ldg(vals + k);
-    G1Affine p; ld_affine_g(p, tab + (v & 0x7FFFFFFFu));
-    madd(acc, p, (v >> 31) != 0);
-  }
-  buckets[b] = acc;
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// block-per-heavy-bucket: strided partial sums + shared-memory tree
+// T = 2^logT threads share a bucket (contiguous slices of its sorted entries) so that the grid has
+// ~2^18 threads with near-identical trip counts whatever the window size; partials[b*T + k] is
+// folded by k_sum_chunks.  The next table point is prefetched into L2 while the current mixed
+// addition (~3 500 instructions) runs.
+__global__ void __launch_bounds__(128)
+k_bucket_acc(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
+             const G1Affine* __restrict__ tab, uint32_t nbuckets, uint32_t logT, uint32_t heavy_cap,
+             G1Xyzz* __restrict__ partials, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = t >> logT, k = t & ((1u << logT) - 1u);
+  if (b >= nbuckets) return;
+  uint32_t s = start[b], e = start[b + 1];
+  uint32_t len = e - s;
+  G1Xyzz acc; set_inf(acc);
+  if ((len >> logT) > heavy_cap) {
+    if (k == 0) { uint32_t slot = atomicAdd(heavy_count, 1u); heavy_list[slot] = b; }
+    partials[t] = acc;            // the heavy kernel overwrites slice 0 with the whole bucket
+    return;
+  }
+  uint32_t lo = s + (uint32_t)(((uint64_t)len * k) >> logT);
+  uint32_t hi = s + (uint32_t)(((uint64_t)len * (k + 1)) >> logT);
+  uint32_t v = 0;
+  if (lo < hi) {
+    v = __ldg(vals + lo);
+    const G1Affine* np = tab + (v & 0x7FFFFFFFu);
+    prefetch_l2(np); prefetch_l2(reinterpret_cast<const char*>(np) + 95);
+  }
+#pragma unroll 1
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t vc = v;
+    if (i + 1 < hi) {
+      v = __ldg(vals + i + 1);
+      const G1Affine* np = tab + (v & 0x7FFFFFFFu);
+      prefetch_l2(np); prefetch_l2(reinterpret_cast<const char*>(np) + 95);
+    }
+    G1Affine p; ld_affine_g(p, tab + (vc & 0x7FFFFFFFu));
+    madd(acc, p, (vc >> 31) != 0);
+  }
+  partials[t] = acc;
+}
+
+// heavy buckets (adversarial inputs: all-equal scalars put n entries in one bucket): HEAVY_BLOCKS
+// blocks share one bucket, each folds its strided entries through a shared-memory tree into
+// heavy_parts[h*HEAVY_BLOCKS + blockIdx.x]; k_heavy_fold sums those into slice 0 of the bucket.
+constexpr int HEAVY_BLOCKS = 32;
+
 __global__ void __launch_bounds__(128)
 k_bucket_heavy(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
-               const G1Affine* __restrict__ tab, G1Xyzz* __restrict__ buckets,
+               const G1Affine* __restrict__ tab, G1Xyzz* __restrict__ heavy_parts,
                const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count) {
   __shared__ G1Xyzz sh[128];
   uint32_t nh = *heavy_count;
-  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+  for (uint32_t h = blockIdx.y; h < nh; h += gridDim.y) {
     uint32_t b = heavy_list[h];
     uint32_t s = start[b], e = start[b + 1];
     G1Xyzz acc; set_inf(acc);
 #pragma unroll 1
-    for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) {
+    for (uint32_t k = s + blockIdx.x * blockDim.x + threadIdx.x; k < e; k += blockDim.x * HEAVY_BLOCKS) {
       uint32_t v = __ldg(vals + k);
       G1Affine p; ld_affine_g(p, tab + (v & 0x7FFFFFFFu));
       madd(acc, p, (v >> 31) != 0);
@@ -124,38 +151,91 @@ k_bucket_heavy(const uint32_t* __restrict__ start, const uint32_t* __restrict__ 
       if (threadIdx.x < st) { G1Xyzz o = sh[threadIdx.x + st]; add(acc, o); sh[threadIdx.x] = acc; }
       __syncthreads();
     }
-    if (threadIdx.x == 0) buckets[b] = acc;
+    if (threadIdx.x == 0) heavy_parts[(size_t)h * HEAVY_BLOCKS + blockIdx.x] = acc;
     __syncthreads();
   }
 }
 
-// ---- 5. reduce ---------------------------------------------------------------------------------
-__device__ __forceinline__ void small_mul(G1Xyzz& o, const G1Xyzz& p, uint32_t m) {
-  G1Xyzz acc; set_inf(acc);
-  if (m == 0 || is_inf(p)) { o = acc; return; }
-  for (int i = 31 - __clz(m); i >= 0; i--) {
-    dbl(acc);
-    if ((m >> i) & 1) add(acc, p);
+__global__ void __launch_bounds__(128)
+k_heavy_fold(const G1Xyzz* __restrict__ heavy_parts, uint32_t logT, G1Xyzz* __restrict__ partials,
+             const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count) {
+  uint32_t nh = *heavy_count;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
+    G1Xyzz acc; set_inf(acc);
+    for (int k = 0; k < HEAVY_BLOCKS; k++) { G1Xyzz o = heavy_parts[(size_t)h * HEAVY_BLOCKS + k]; add(acc, o); }
+    partials[(size_t)heavy_list[h] << logT] = acc;
   }
-  o = acc;
 }
 
-// out[k] = sum_{l<L} (k L + l + 1) * B[k L + l]
-__global__ void __launch_bounds__(128)
-k_bucket_reduce(const G1Xyzz* __restrict__ buckets, uint32_t M, uint32_t L, G1Xyzz* __restrict__ out) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t chunks = (M + L - 1) / L;
-  if (k >= chunks) return;
-  G1Xyzz run, acc; set_inf(run); set_inf(acc);
-#pragma unroll 1
-  for (int l = (int)L - 1; l >= 0; l--) {
-    uint32_t idx = k * L + (uint32_t)l;
-    if (idx < M) { G1Xyzz b = buckets[idx]; add(run, b); }
-    add(acc, run);
+// ---- 5. reduce ---------------------------------------------------------------------------------
+// sum_i (i+1) * A_i over M buckets, warp-cooperatively.  A warp owns 32 consecutive buckets, one per
+// lane: a 5-step suffix scan through shuffles gives R_l = sum_{m>=l} A_m, hence S = R_0 and
+// W = sum_l l*A_l = sum_{l>=1} R_l (a 5-step tree).  Then sum_i i*A_i = sum_k W_k + 32 * sum_k k*S_k
+// and the second term is the same problem on the 32x smaller array S: log_32(M) levels of ten
+// sequential additions each instead of a 2L-long running sum per thread.
+__device__ __forceinline__ void shfl_down_pt(G1Xyzz& o, const G1Xyzz& p, int d) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    o.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
+    o.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
+    o.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
+    o.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], d);
   }
-  G1Xyzz P; small_mul(P, run, k * L);
-  add(acc, P);
-  out[k] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+k_reduce_warp(const G1Xyzz* __restrict__ A, uint32_t M, G1Xyzz* __restrict__ W_out, G1Xyzz* __restrict__ S_out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t chunks = (M + 31) >> 5;
+  if (k >= chunks) return;                       // whole warps exit together
+  const uint32_t idx = k * 32 + lane;
+  G1Xyzz R;
+  if (idx < M) R = A[idx]; else set_inf(R);
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {             // suffix scan
+    G1Xyzz o; shfl_down_pt(o, R, d);
+    if (lane + d < 32) add(R, o);
+  }
+  if (lane == 0) S_out[k] = R;
+  G1Xyzz X = R;
+  if (lane == 0) set_inf(X);
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {            // tree sum of R_1..R_31
+    G1Xyzz o; shfl_down_pt(o, X, d);
+    if (lane < d) add(X, o);
+  }
+  if (lane == 0) W_out[k] = X;
+}
+
+// out[k] = sum of in[32k .. 32k+32), one warp per output
+__global__ void __launch_bounds__(128)
+k_sum_warp(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t chunks = (count + 31) >> 5;
+  if (k >= chunks) return;
+  const uint64_t idx = k * 32 + lane;
+  G1Xyzz X;
+  if (idx < count) X = in[idx]; else set_inf(X);
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    G1Xyzz o; shfl_down_pt(o, X, d);
+    if (lane < d) add(X, o);
+  }
+  if (lane == 0) out[k] = X;
+}
+
+// result = S_total + Wsum_0 + 32*(Wsum_1 + 32*(Wsum_2 + ...)) : single thread, a handful of operations
+__global__ void k_reduce_final(const G1Xyzz* __restrict__ lvl, int nlevels, const G1Xyzz* __restrict__ s_total,
+                               G1Xyzz* __restrict__ out) {
+  G1Xyzz acc = lvl[nlevels - 1];
+  for (int l = nlevels - 2; l >= 0; l--) {
+    for (int k = 0; k < 5; k++) dbl(acc);
+    G1Xyzz w = lvl[l]; add(acc, w);
+  }
+  G1Xyzz st = s_total[0]; add(acc, st);
+  out[0] = acc;
 }
 
 // out[k] = sum of in[k L .. k L + L)
@@ -186,22 +266,51 @@ int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* o
     KZG_LAUNCHED(ctx);
     return KZG_OK;
   }
-  const uint32_t L = 8;
   void *a, *b;
-  uint64_t c1 = (count + L - 1) / L;
+  uint64_t c1 = (count + 31) / 32;
   KZG_TRY(scratch_get(ctx, SCR_RED_A, (c1 + 1) * sizeof(G1Xyzz), &a));
-  KZG_TRY(scratch_get(ctx, SCR_RED_B, ((c1 + L - 1) / L + 1) * sizeof(G1Xyzz), &b));
+  KZG_TRY(scratch_get(ctx, SCR_RED_B, ((c1 + 31) / 32 + 1) * sizeof(G1Xyzz), &b));
   const G1Xyzz* src = in_dev;
   G1Xyzz* bufs[2] = {reinterpret_cast<G1Xyzz*>(a), reinterpret_cast<G1Xyzz*>(b)};
   int which = 0;
   while (true) {
-    uint64_t chunks = (count + L - 1) / L;
+    uint64_t chunks = (count + 31) / 32;
     G1Xyzz* dst = chunks == 1 ? out_dev : bufs[which];
-    k_sum_chunks<<<blocks_for(chunks, 128), 128, 0, ctx->stream>>>(src, count, L, dst);
+    k_sum_warp<<<blocks_for(chunks * 32, 128), 128, 0, ctx->stream>>>(src, count, dst);
     KZG_LAUNCHED(ctx);
     if (chunks == 1) break;
     src = dst; count = chunks; which ^= 1;
   }
+  return KZG_OK;
+}
+
+// sum_b (b+1) * buckets[b] -> result_dev
+static int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* buckets, uint32_t M, G1Xyzz* result_dev) {
+  // level sizes M -> ceil(M/32) -> ... -> 1
+  uint32_t sizes[8]; int nlev = 0;
+  for (uint32_t m = M;; ) { uint32_t k = (m + 31) / 32; sizes[nlev++] = k; if (k == 1) break; m = k; }
+  size_t tot = 0;
+  for (int l = 0; l < nlev; l++) tot += sizes[l];
+  void* ws;
+  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, (2 * tot + 16) * sizeof(G1Xyzz), &ws));
+  G1Xyzz* W = reinterpret_cast<G1Xyzz*>(ws);
+  G1Xyzz* S = W + tot;
+  G1Xyzz* lvl = S + tot;
+  const G1Xyzz* cur = buckets;
+  uint32_t m = M; size_t off = 0;
+  const G1Xyzz* s_last = nullptr;
+  for (int l = 0; l < nlev; l++) {
+    k_reduce_warp<<<blocks_for((uint64_t)sizes[l] * 32, 128), 128, 0, ctx->stream>>>(cur, m, W + off, S + off);
+    KZG_LAUNCHED(ctx);
+    cur = S + off; s_last = S + off; m = sizes[l]; off += sizes[l];
+  }
+  off = 0;
+  for (int l = 0; l < nlev; l++) {
+    KZG_TRY(sum_points(ctx, W + off, sizes[l], lvl + l));
+    off += sizes[l];
+  }
+  k_reduce_final<<<1, 1, 0, ctx->stream>>>(lvl, nlev, s_last, result_dev);
+  KZG_LAUNCHED(ctx);
   return KZG_OK;
 }
 
@@ -219,7 +328,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   if ((uint64_t)W * s->n >= (1ull << 31) || total >= (1ull << 32))
     return fail(ctx, KZG_E_BAD_ARG, "msm too large for 31-bit table indices");
 
-  void *ka, *kb, *va, *vb, *st, *bk, *hv, *red;
+  void *ka, *kb, *va, *vb, *st, *bk, *hv;
   KZG_TRY(scratch_get(ctx, SCR_KEYS_A, total * 4, &ka));
   KZG_TRY(scratch_get(ctx, SCR_KEYS_B, total * 4, &kb));
   KZG_TRY(scratch_get(ctx, SCR_VALS_A, total * 4, &va));
@@ -227,7 +336,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   KZG_TRY(scratch_get(ctx, SCR_BUCKET_START, ((size_t)half + 3) * 4, &st));
   KZG_TRY(scratch_get(ctx, SCR_BUCKETS, (size_t)half * sizeof(G1Xyzz), &bk));
   const uint32_t heavy_cap = (uint32_t)ctx->opt_heavy_cap;
-  size_t heavy_max = total / heavy_cap + 2;
+  size_t heavy_max = total / heavy_cap + 2 + 64;
   KZG_TRY(scratch_get(ctx, SCR_HEAVY, (heavy_max + 1) * 4, &hv));
   uint32_t* heavy_count = reinterpret_cast<uint32_t*>(hv);
   uint32_t* heavy_list = heavy_count + 1;
@@ -253,24 +362,37 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   KZG_LAUNCHED(ctx);
   KZG_CUDA_OK(ctx, cudaMemsetAsync(heavy_count, 0, 4, ctx->stream));
 
+  // threads per bucket: aim for ~2^18 accumulate threads
+  uint32_t logT = 0;
+  if (ctx->opt_acc_split >= 0) logT = (uint32_t)ctx->opt_acc_split;
+  else while ((half << logT) < (1u << 18) && (total >> (c - 1 + logT)) > 32) logT++;
+  const uint32_t T = 1u << logT;
+  void* parts = bk;
+  if (logT) KZG_TRY(scratch_get(ctx, SCR_PARTIALS, ((size_t)half << logT) * sizeof(G1Xyzz), &parts));
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  k_bucket_acc<<<blocks_for(half, 128), 128, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(st),
-                                                               reinterpret_cast<uint32_t*>(vb), s->msm_tab, half, heavy_cap,
-                                                               reinterpret_cast<G1Xyzz*>(bk), heavy_list, heavy_count);
+  k_bucket_acc<<<blocks_for((uint64_t)half << logT, 128), 128, 0, ctx->stream>>>(
+      reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb), s->msm_tab, half, logT, heavy_cap,
+      reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
   KZG_LAUNCHED(ctx);
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-  k_bucket_heavy<<<32, 128, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb),
-                                              s->msm_tab, reinterpret_cast<G1Xyzz*>(bk), heavy_list, heavy_count);
-  KZG_LAUNCHED(ctx);
+  {
+    void* hp;
+    KZG_TRY(scratch_get(ctx, SCR_HEAVY_PARTS, heavy_max * HEAVY_BLOCKS * sizeof(G1Xyzz), &hp));
+    k_bucket_heavy<<<dim3(HEAVY_BLOCKS, 16), 128, 0, ctx->stream>>>(
+        reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb), s->msm_tab, reinterpret_cast<G1Xyzz*>(hp),
+        heavy_list, heavy_count);
+    KZG_LAUNCHED(ctx);
+    k_heavy_fold<<<8, 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(hp), logT, reinterpret_cast<G1Xyzz*>(parts),
+                                             heavy_list, heavy_count);
+    KZG_LAUNCHED(ctx);
+  }
+  if (logT) {
+    k_sum_chunks<<<blocks_for(half, 128), 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(parts), (uint64_t)half << logT, T,
+                                                                 reinterpret_cast<G1Xyzz*>(bk));
+    KZG_LAUNCHED(ctx);
+  }
 
-  uint32_t L = (uint32_t)ctx->opt_reduce_chunk;
-  if (L < 2) L = 2;
-  uint32_t chunks = (half + L - 1) / L;
-  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, (size_t)chunks * sizeof(G1Xyzz), &red));
-  k_bucket_reduce<<<blocks_for(chunks, 128), 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(bk), half, L,
-                                                                    reinterpret_cast<G1Xyzz*>(red));
-  KZG_LAUNCHED(ctx);
-  KZG_TRY(sum_points(ctx, reinterpret_cast<G1Xyzz*>(red), chunks, result_dev));
+  KZG_TRY(reduce_buckets(ctx, reinterpret_cast<G1Xyzz*>(bk), half, result_dev));
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   return KZG_OK;
 }
