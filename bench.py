@@ -219,6 +219,10 @@ def run_ours(args):
 
     imad_peak = ctx.probe_imad_peak()
     fq_peak = ctx.probe_fq_mul()
+    blob = None
+    if args.blobs > 0:
+        setup.close()
+        blob = blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, args.blobs, 2, args.fixed_window)
 
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -261,28 +265,87 @@ def run_ours(args):
                          "hbm": {"achieved": hbm_bytes / (acc * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_bytes / (acc * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peaks_src}},
         }
+        if blob is not None:
+            line["blob_batch"] = blob
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": "points/s", "cores": threads, "kind": "port",
                                     "sample": f"{1024 * threads}-point prefix of the same scalars, reference naive loop "
                                               f"(src/polynomial.rs:207-212) split over {threads} threads, {cpu_dt:.2f} s"}
         print(json.dumps(line))
-    setup.close()
+    if blob is None:
+        setup.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, blobs_total, steps, fixed_window):
+    """Secondary metric (BASELINE config C4): 4096 blobs x 4096 coefficients, commit + evaluation proof per
+    blob, sharded by BLOB across ranks (no data-path collective); blob (commit+proof)/s."""
+    n = 4096
+    first, count = rank * (blobs_total // world), blobs_total // world
+    setup = ctx.setup_generate(synthetic.BENCH_SECRET_BE, n)
+    t0 = time.perf_counter()
+    setup.prepare_fixed(n, fixed_window)
+    ctx.sync()
+    table_s = time.perf_counter() - t0
+    host = torch.from_numpy(synthetic.scalar_stream(0xC4, count * n, start=first * n)).pin_memory()
+    zs_host = torch.from_numpy(synthetic.scalar_stream(0xC4F, count, start=first)).pin_memory()
+    coeffs = host.to(dev)
+    zs = zs_host.to(dev)
+    commits = torch.zeros(count * 48, dtype=torch.uint8, device=dev)
+    proofs = torch.zeros(count * 48, dtype=torch.uint8, device=dev)
+    ys = torch.zeros(count * 32, dtype=torch.uint8, device=dev)
+    out_c = torch.zeros(count * 48, dtype=torch.uint8).pin_memory()
+    out_p = torch.zeros(count * 48, dtype=torch.uint8).pin_memory()
+    out_y = torch.zeros(count * 32, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_dev():
+        ctx.commit_batch_dev(setup, coeffs.data_ptr(), count, n, commits.data_ptr())
+        ctx.open_batch_dev(setup, coeffs.data_ptr(), count, n, zs.data_ptr(), ys.data_ptr(), proofs.data_ptr())
+        ctx.sync()
+
+    def step_e2e():
+        ctx.commit_batch(setup, host.data_ptr(), count, n, out=out_c.data_ptr())
+        ctx.open_batch(setup, host.data_ptr(), count, n, zs_host.data_ptr(), y_out=out_y.data_ptr(), proofs_out=out_p.data_ptr())
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(); ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        ctx.sync(); torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    step_dev()
+    ms_dev = timed(step_dev, steps) / steps
+    step_e2e()
+    ms_e2e = timed(step_e2e, steps) / steps
+    same = bytes(commits.cpu().numpy().tobytes()) == bytes(out_c.numpy().tobytes()) and \
+        bytes(proofs.cpu().numpy().tobytes()) == bytes(out_p.numpy().tobytes())
+    setup.close()
+    W = (256 + fixed_window - 1) // fixed_window
+    return {"metric": "blob_commit_plus_proof_per_s", "value": blobs_total / (ms_dev * 1e-3), "unit": "blobs/s",
+            "ms_per_batch": ms_dev, "e2e": {"value": blobs_total / (ms_e2e * 1e-3), "unit": "blobs/s", "ms_per_batch": ms_e2e,
+                                            "h2d_bytes_per_batch": 2 * blobs_total * n * 32 + blobs_total * 32,
+                                            "d2h_bytes_per_batch": blobs_total * 128},
+            "config": {"workload": f"{blobs_total} blobs x {n} coefficients (BASELINE config C4), commit + proof, sharded by blob",
+                       "fixed_base_window_bits": fixed_window, "lookups_per_coefficient": W,
+                       "table_gib": round(n * W * (1 << (fixed_window - 1)) * 96 / 2**30, 2), "table_build_s": round(table_s, 2)},
+            "dev_equals_e2e": bool(same), "scaling": "weak" if world > 1 else "n/a"}
+
+
 def setup_windows(ctx, setup, n, requested):
-    """window geometry actually used (mirrors auto_msm_window / windows_for in csrc)."""
-    if requested:
-        c = requested
-    else:
-        best, best_cost = 8, 1e300
-        for c in range(6, 23):
-            cost = ((256 + c - 1) // c) * n + 3.0 * 1.4 * (1 << (c - 1))
-            if cost < best_cost:
-                best, best_cost = c, cost
-        c = best
+    """window geometry actually used (mirrors auto_msm_window / windows_for in csrc/setup.cu)."""
+    c = requested if requested else 16   # auto_msm_window(n >= 2^17) == 16
     return {"c": c, "W": (256 + c - 1) // c}
 
 
@@ -293,6 +356,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--window", type=int, default=int(os.environ.get("KZG_WINDOW", "0")))
+    ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BLOBS", "4096")),
+                    help="size of the secondary blob batch (0 = skip)")
+    ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "10")))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -1,0 +1,197 @@
+// kzg_b200.hpp — header-only C++ host mirror of the reference's public Rust API over the C ABI.
+//
+// The reference is compiled code (Rust); with no Rust toolchain in this image the host side above the
+// C ABI is C++ with the SAME module / type / method names and error messages:
+//   scalar::Scalar                    src/scalar.rs
+//   curves::G1Point                   src/curves.rs:10-183
+//   trusted_setup::{SetupArtifactsGenerator, SetupArtifact, TrustedSetup}   src/trusted_setup.rs
+//   polynomial::{Polynomial, Evaluation}                                    src/polynomial.rs
+// anyhow::Error becomes kzg::Error (what() carries the reference's message).  One FFI call per bulk op.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "kzg_b200.h"
+
+namespace kzg {
+
+struct Error : std::runtime_error {
+  int32_t status;
+  Error(int32_t st, const std::string& msg) : std::runtime_error(msg), status(st) {}
+};
+
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    int32_t st = kzg_ctx_create(&h_, device);
+    if (st != KZG_OK) throw Error(st, "kzg_ctx_create failed: no usable CUDA device (there is no CPU fallback)");
+  }
+  ~Context() { kzg_ctx_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  kzg_ctx* get() const { return h_; }
+  void check(int32_t st) const {
+    if (st != KZG_OK) {
+      std::string m = kzg_last_error(h_);
+      throw Error(st, m.empty() ? kzg_status_string(st) : m);
+    }
+  }
+ private:
+  kzg_ctx* h_ = nullptr;
+};
+
+namespace scalar {
+class Scalar {
+ public:
+  Scalar() : le_{} {}
+  static Scalar from_le_bytes(const std::array<uint8_t, 32>& b) { Scalar s; kzg_fr_reduce(b.data(), s.le_.data()); return s; }
+  static Scalar from_be_bytes(const std::array<uint8_t, 32>& b) {
+    std::array<uint8_t, 32> le; for (int i = 0; i < 32; i++) le[i] = b[31 - i];
+    return from_le_bytes(le);
+  }
+  // impl From<i128>: a > 0 -> a, a <= 0 -> r - |a| (src/scalar.rs:27-48)
+  static Scalar from_i128(__int128 a) {
+    unsigned __int128 mag = a < 0 ? (unsigned __int128)(-(a + 1)) + 1 : (unsigned __int128)a;
+    std::array<uint8_t, 32> le{}; for (int i = 0; i < 16; i++) le[i] = (uint8_t)(mag >> (8 * i));
+    Scalar s = from_le_bytes(le);
+    return a > 0 ? s : s.neg();
+  }
+  std::array<uint8_t, 32> to_le_bytes() const { return le_; }
+  std::array<uint8_t, 32> to_be_bytes() const { std::array<uint8_t, 32> b; for (int i = 0; i < 32; i++) b[i] = le_[31 - i]; return b; }
+  Scalar mul(const Scalar& o) const { Scalar r; kzg_fr_mul(le_.data(), o.le_.data(), r.le_.data()); return r; }
+  Scalar add(const Scalar& o) const { Scalar r; kzg_fr_add(le_.data(), o.le_.data(), r.le_.data()); return r; }
+  Scalar sub(const Scalar& o) const { Scalar r; kzg_fr_sub(le_.data(), o.le_.data(), r.le_.data()); return r; }
+  Scalar neg() const { Scalar r; kzg_fr_neg(le_.data(), r.le_.data()); return r; }
+  Scalar pow(size_t n) const { Scalar r; kzg_fr_pow(le_.data(), n, r.le_.data()); return r; }
+  bool is_zero() const { for (auto b : le_) if (b) return false; return true; }
+  bool operator==(const Scalar& o) const { return le_ == o.le_; }
+  bool operator!=(const Scalar& o) const { return !(*this == o); }
+ private:
+  std::array<uint8_t, 32> le_;
+};
+}  // namespace scalar
+
+namespace curves {
+class G1Point {
+ public:
+  // Deserialize (src/curves.rs:112-183)
+  static G1Point from_compressed(const uint8_t* b, size_t len) {
+    if (len != 48) throw Error(KZG_E_BAD_LENGTH, "Invalid length, expected 48, got " + std::to_string(len));
+    if (kzg_g1_check(b) != KZG_OK) throw Error(KZG_E_BAD_POINT, "Got error while uncompressing");
+    G1Point p; std::copy(b, b + 48, p.c_.begin()); return p;
+  }
+  static G1Point from_scalar(const scalar::Scalar& a) { G1Point p; kzg_g1_from_scalar(a.to_le_bytes().data(), p.c_.data()); return p; }
+  static G1Point from_i128(__int128 a) {
+    G1Point p = from_scalar(scalar::Scalar::from_i128(a < 0 ? -a : a));
+    return a < 0 ? from_scalar(scalar::Scalar()).sub(p) : p;
+  }
+  G1Point add(const G1Point& b) const { G1Point r; kzg_g1_add(c_.data(), b.c_.data(), r.c_.data()); return r; }
+  G1Point sub(const G1Point& b) const { G1Point r; kzg_g1_sub(c_.data(), b.c_.data(), r.c_.data()); return r; }
+  G1Point mult(const scalar::Scalar& a) const { G1Point r; kzg_g1_mul(c_.data(), a.to_le_bytes().data(), r.c_.data()); return r; }
+  const std::array<uint8_t, 48>& compressed() const { return c_; }   // Serialize (src/curves.rs:99-110)
+  bool operator==(const G1Point& o) const { return c_ == o.c_; }
+  static G1Point raw(const uint8_t* b) { G1Point p; std::copy(b, b + 48, p.c_.begin()); return p; }
+ private:
+  std::array<uint8_t, 48> c_{};
+};
+}  // namespace curves
+
+namespace trusted_setup {
+struct SetupArtifact { curves::G1Point g1; };
+
+// Vec<SetupArtifact> + its device-resident copy
+class TrustedSetup {
+ public:
+  TrustedSetup(std::shared_ptr<Context> ctx, kzg_setup* h) : ctx_(std::move(ctx)), h_(h) {}
+  ~TrustedSetup() { kzg_setup_destroy(h_); }
+  TrustedSetup(const TrustedSetup&) = delete;
+  size_t len() const { return kzg_setup_len(h_); }
+  SetupArtifact at(size_t i) const {
+    uint8_t b[48]; ctx_->check(kzg_setup_export_g1(ctx_->get(), h_, i, 1, b));
+    return SetupArtifact{curves::G1Point::raw(b)};
+  }
+  void prepare_msm(int window_bits = 0) { ctx_->check(kzg_setup_prepare_msm(ctx_->get(), h_, window_bits)); }
+  void prepare_fixed(size_t n_points, int window_bits = 0) { ctx_->check(kzg_setup_prepare_fixed(ctx_->get(), h_, n_points, window_bits)); }
+  const std::shared_ptr<Context>& ctx() const { return ctx_; }
+  kzg_setup* handle() const { return h_; }
+ private:
+  std::shared_ptr<Context> ctx_;
+  kzg_setup* h_;
+};
+
+class SetupArtifactsGenerator {
+ public:
+  SetupArtifactsGenerator(std::shared_ptr<Context> ctx, const std::array<uint8_t, 32>& secret_be) : ctx_(std::move(ctx)), secret_(secret_be) {}
+  // .take(n).collect()  (src/trusted_setup.rs:40-78)
+  std::unique_ptr<TrustedSetup> take(size_t n) const {
+    kzg_setup* h = nullptr;
+    ctx_->check(kzg_setup_generate(ctx_->get(), secret_.data(), 0, n, &h));
+    return std::make_unique<TrustedSetup>(ctx_, h);
+  }
+ private:
+  std::shared_ptr<Context> ctx_;
+  std::array<uint8_t, 32> secret_;
+};
+}  // namespace trusted_setup
+
+namespace polynomial {
+using scalar::Scalar;
+class Evaluation;
+
+class Polynomial {
+ public:
+  // TryFrom<Vec<Scalar>>: trailing zeros trimmed, an all-zero input keeps one coefficient (src/polynomial.rs:55-75)
+  static Polynomial try_from(std::vector<Scalar> v) {
+    size_t last = 0;
+    for (size_t i = 0; i < v.size(); i++) if (!v[i].is_zero()) last = i;
+    if (!v.empty()) v.resize(last + 1);
+    return Polynomial(std::move(v));
+  }
+  static Polynomial try_from_i128(const std::vector<__int128>& v) {
+    std::vector<Scalar> s; for (auto a : v) s.push_back(Scalar::from_i128(a));
+    return try_from(std::move(s));
+  }
+  static Polynomial from(const Scalar& c) { return Polynomial(c.is_zero() ? std::vector<Scalar>{} : std::vector<Scalar>{c}); }
+  uint32_t degree() const { return coefficients_.empty() ? 0 : (uint32_t)(coefficients_.size() - 1); }
+  const std::vector<Scalar>& coefficients() const { return coefficients_; }
+
+  inline Evaluation evaluate(const Context& ctx, const Scalar& x) const;
+  // Polynomial::commit (src/polynomial.rs:200-215)
+  curves::G1Point commit(const trusted_setup::TrustedSetup& setup) const {
+    auto b = bytes(); uint8_t out[48];
+    setup.ctx()->check(kzg_commit(setup.ctx()->get(), setup.handle(), b.data(), coefficients_.size(), out));
+    return curves::G1Point::raw(out);
+  }
+  std::vector<uint8_t> bytes() const {
+    std::vector<uint8_t> b(coefficients_.size() * 32);
+    for (size_t i = 0; i < coefficients_.size(); i++) { auto le = coefficients_[i].to_le_bytes(); std::copy(le.begin(), le.end(), b.begin() + 32 * i); }
+    return b;
+  }
+ private:
+  explicit Polynomial(std::vector<Scalar> c) : coefficients_(std::move(c)) {}
+  std::vector<Scalar> coefficients_;
+};
+
+class Evaluation {
+ public:
+  Scalar point, result;
+  // Evaluation::generate_proof (src/polynomial.rs:260-269)
+  curves::G1Point generate_proof(const Polynomial& p, const trusted_setup::TrustedSetup& setup) const {
+    auto b = p.bytes(); uint8_t y[32], out[48];
+    setup.ctx()->check(kzg_open(setup.ctx()->get(), setup.handle(), b.data(), p.coefficients().size(), point.to_le_bytes().data(),
+                                result.to_le_bytes().data(), y, out));
+    return curves::G1Point::raw(out);
+  }
+};
+
+inline Evaluation Polynomial::evaluate(const Context& ctx, const Scalar& x) const {
+  auto b = bytes(); std::array<uint8_t, 32> y;
+  ctx.check(kzg_evaluate(ctx.get(), b.data(), coefficients_.size(), x.to_le_bytes().data(), y.data()));
+  return Evaluation{x, Scalar::from_le_bytes(y)};
+}
+}  // namespace polynomial
+
+}  // namespace kzg

@@ -8,6 +8,7 @@
 // shared inversion per thread (Montgomery's trick) and kept device-resident.
 // Also here: G1 (de)serialisation kernels (Serialize / Deserialize for G1Point,
 // src/curves.rs:99-183) and the per-setup tables used by the MSM kernels.
+#include <cmath>
 #include "engine.cuh"
 
 namespace kzg {
@@ -311,10 +312,23 @@ int32_t setup_generate_dev(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t f
 }
 
 int auto_msm_window(uint64_t n) {
-  // cost model: W*n mixed additions + ~3 * 2^(c-1) full additions for the bucket reduction
-  int best = 8; double best_cost = 1e300;
-  for (int c = 6; c <= 22; c++) {
-    double cost = (double)windows_for(c) * (double)n + 3.0 * 1.4 * (double)(1ull << (c - 1));
+  // Measured on B200 (profiles/sweep_window_r01.txt): with folded windows the accumulate time is flat in c
+  // between 14 and 18 bits, the tail grows with the bucket count, and window sizes whose TOP window holds
+  // only a few bits funnel n / 2^t entries into a handful of buckets (the heavy path).  Prefer c = 16
+  // (16 windows, 15-bit top window) for large n; scale down so that ~2^18 accumulate threads still get
+  // >= 32 entries each for small n.
+  if (n >= (1ull << 17)) return 16;
+  int best = 4; double best_cost = 1e300;
+  for (int c = 4; c <= 16; c++) {
+    int W = windows_for(c);
+    int top_bits = 255 - c * (W - 1);
+    double entries = (double)W * (double)n;
+    double buckets = (double)(1ull << (c - 1));
+    double per_thread = entries / (buckets < 262144.0 ? 262144.0 : buckets);
+    if (per_thread < 8) per_thread = 8;
+    double cost = entries * (1.0 + 2.0 / sqrt(per_thread)) + 8.0 * buckets;
+    if (top_bits < c - 4) cost += (double)n;   // skewed top window -> heavy buckets
+    cost += 40000.0 * (c > 10 ? (c - 10) / 5.0 : 0.0);  // extra reduction level
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;

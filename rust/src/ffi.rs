@@ -1,0 +1,29 @@
+//! Raw bindings of include/kzg_b200.h (the subset the drop-in needs).
+#![allow(non_camel_case_types)]
+use std::os::raw::c_char;
+
+#[repr(C)] pub struct kzg_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct kzg_setup { _p: [u8; 0] }
+
+pub const KZG_OK: i32 = 0;
+pub const KZG_E_DEGREE_TOO_HIGH: i32 = 1;
+pub const KZG_E_CONSTANT_POLY: i32 = 2;
+pub const KZG_E_REMAINDER_NONZERO: i32 = 3;
+
+extern "C" {
+    pub fn kzg_ctx_create(out: *mut *mut kzg_ctx, device_id: i32) -> i32;
+    pub fn kzg_ctx_destroy(ctx: *mut kzg_ctx);
+    pub fn kzg_last_error(ctx: *const kzg_ctx) -> *const c_char;
+    pub fn kzg_setup_generate(ctx: *mut kzg_ctx, secret_be: *const u8, first: u64, n: u64, out: *mut *mut kzg_setup) -> i32;
+    pub fn kzg_setup_import_g1(ctx: *mut kzg_ctx, g1_c48: *const u8, n: u64, out: *mut *mut kzg_setup) -> i32;
+    pub fn kzg_setup_export_g1(ctx: *mut kzg_ctx, s: *const kzg_setup, first: u64, count: u64, out_c48: *mut u8) -> i32;
+    pub fn kzg_setup_len(s: *const kzg_setup) -> u64;
+    pub fn kzg_setup_destroy(s: *mut kzg_setup);
+    pub fn kzg_commit(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, n: u64, out_c48: *mut u8) -> i32;
+    pub fn kzg_evaluate(ctx: *mut kzg_ctx, coeffs_le32: *const u8, n: u64, z_le: *const u8, y_le: *mut u8) -> i32;
+    pub fn kzg_open(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, n: u64, z_le: *const u8,
+                    y_expected_le: *const u8, y_out_le: *mut u8, proof_c48: *mut u8) -> i32;
+    pub fn kzg_commit_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64, out_c48: *mut u8) -> i32;
+    pub fn kzg_open_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64,
+                          z_le32: *const u8, y_le32: *mut u8, proofs_c48: *mut u8) -> i32;
+}
