@@ -39,6 +39,7 @@ struct kzg_ctx {
   int opt_reduce_chunk = 16;
   int opt_heavy_cap = 1024;
   int opt_acc_split = -1;              // log2(threads per bucket), -1 = auto
+  int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
 };
 
@@ -112,6 +113,8 @@ int32_t build_fixed_table(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int c);
 // result_dev: one G1Xyzz (device).  Uses s->msm_tab (built on demand).
 int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
                    G1Xyzz* result_dev);
+// sum_b (b+1) * A_b, A_b = sum_k parts[b*T + k] with T = 2^logT partials per bucket (msm_tail.cu)
+int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, G1Xyzz* result_dev);
 // sum `count` XYZZ points (device) into out_dev[0]
 int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev);
 // XYZZ (device) x count -> 48-byte compressed (device)

@@ -96,15 +96,30 @@ inline void host_sub_mod(uint32_t* o, const uint32_t* a, const uint32_t* b, cons
 }
 
 // ---- dispatch ---------------------------------------------------------------------
-KZG_HD void mul(Fq& o, const Fq& a, const Fq& b) {
+#if defined(__CUDACC__) && defined(KZG_FQ_NOINLINE)
+// one out-of-line copy of the product per translation unit (operands travel in registers): for the
+// latency-bound kernels, where instruction fetch of the inlined 6 KB sequence is the bottleneck
+static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) {
+  Fq o;
 #if defined(__CUDA_ARCH__)
+  fq_mul_ptx(o.v, a.v, b.v);
+#endif
+  return o;
+}
+#endif
+KZG_HD void mul(Fq& o, const Fq& a, const Fq& b) {
+#if defined(__CUDA_ARCH__) && defined(KZG_FQ_NOINLINE)
+  o = fq_mul_call(a, b);
+#elif defined(__CUDA_ARCH__)
   fq_mul_ptx(o.v, a.v, b.v);
 #else
   host_mont_mul<12>(o.v, a.v, b.v, h_FQ_P, FQ_INV32);
 #endif
 }
 KZG_HD void sqr(Fq& o, const Fq& a) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(KZG_FQ_NOINLINE)
+  o = fq_mul_call(a, a);
+#elif defined(__CUDA_ARCH__)
   fq_sqr_ptx(o.v, a.v);
 #else
   host_mont_mul<12>(o.v, a.v, a.v, h_FQ_P, FQ_INV32);

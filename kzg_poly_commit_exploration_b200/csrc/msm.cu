@@ -16,6 +16,9 @@
 //                 W_k and S_k, adds (k L) * S_k by a short double-and-add, then a tree sum.
 // Integer-multiply bound: 3 000 wide multiply-adds per bucket addition, 96 B of HBM per addition.
 #include <cub/device/device_radix_sort.cuh>
+#ifdef KZG_ACC_NOINLINE
+#define KZG_FQ_NOINLINE 1
+#endif
 #include "engine.cuh"
 
 namespace kzg {
@@ -86,7 +89,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // ~2^18 threads with near-identical trip counts whatever the window size; partials[b*T + k] is
 // folded by k_sum_chunks.  The next table point is prefetched into L2 while the current mixed
 // addition (~3 500 instructions) runs.
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_bucket_acc(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
              const G1Affine* __restrict__ tab, uint32_t nbuckets, uint32_t logT, uint32_t heavy_cap,
              G1Xyzz* __restrict__ partials, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
@@ -167,152 +171,12 @@ k_heavy_fold(const G1Xyzz* __restrict__ heavy_parts, uint32_t logT, G1Xyzz* __re
   }
 }
 
-// ---- 5. reduce ---------------------------------------------------------------------------------
-// sum_i (i+1) * A_i over M buckets, warp-cooperatively.  A warp owns 32 consecutive buckets, one per
-// lane: a 5-step suffix scan through shuffles gives R_l = sum_{m>=l} A_m, hence S = R_0 and
-// W = sum_l l*A_l = sum_{l>=1} R_l (a 5-step tree).  Then sum_i i*A_i = sum_k W_k + 32 * sum_k k*S_k
-// and the second term is the same problem on the 32x smaller array S: log_32(M) levels of ten
-// sequential additions each instead of a 2L-long running sum per thread.
-__device__ __forceinline__ void shfl_down_pt(G1Xyzz& o, const G1Xyzz& p, int d) {
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    o.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
-    o.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
-    o.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
-    o.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], d);
-  }
-}
-
-__global__ void __launch_bounds__(128)
-k_reduce_warp(const G1Xyzz* __restrict__ A, uint32_t M, G1Xyzz* __restrict__ W_out, G1Xyzz* __restrict__ S_out) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t chunks = (M + 31) >> 5;
-  if (k >= chunks) return;                       // whole warps exit together
-  const uint32_t idx = k * 32 + lane;
-  G1Xyzz R;
-  if (idx < M) R = A[idx]; else set_inf(R);
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {             // suffix scan
-    G1Xyzz o; shfl_down_pt(o, R, d);
-    if (lane + d < 32) add(R, o);
-  }
-  if (lane == 0) S_out[k] = R;
-  G1Xyzz X = R;
-  if (lane == 0) set_inf(X);
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {            // tree sum of R_1..R_31
-    G1Xyzz o; shfl_down_pt(o, X, d);
-    if (lane < d) add(X, o);
-  }
-  if (lane == 0) W_out[k] = X;
-}
-
-// out[k] = sum of in[32k .. 32k+32), one warp per output
-__global__ void __launch_bounds__(128)
-k_sum_warp(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ out) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t chunks = (count + 31) >> 5;
-  if (k >= chunks) return;
-  const uint64_t idx = k * 32 + lane;
-  G1Xyzz X;
-  if (idx < count) X = in[idx]; else set_inf(X);
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    G1Xyzz o; shfl_down_pt(o, X, d);
-    if (lane < d) add(X, o);
-  }
-  if (lane == 0) out[k] = X;
-}
-
-// result = S_total + Wsum_0 + 32*(Wsum_1 + 32*(Wsum_2 + ...)) : single thread, a handful of operations
-__global__ void k_reduce_final(const G1Xyzz* __restrict__ lvl, int nlevels, const G1Xyzz* __restrict__ s_total,
-                               G1Xyzz* __restrict__ out) {
-  G1Xyzz acc = lvl[nlevels - 1];
-  for (int l = nlevels - 2; l >= 0; l--) {
-    for (int k = 0; k < 5; k++) dbl(acc);
-    G1Xyzz w = lvl[l]; add(acc, w);
-  }
-  G1Xyzz st = s_total[0]; add(acc, st);
-  out[0] = acc;
-}
-
-// out[k] = sum of in[k L .. k L + L)
-__global__ void __launch_bounds__(128)
-k_sum_chunks(const G1Xyzz* __restrict__ in, uint64_t count, uint32_t L, G1Xyzz* __restrict__ out) {
-  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t chunks = (count + L - 1) / L;
-  if (k >= chunks) return;
-  G1Xyzz acc; set_inf(acc);
-#pragma unroll 1
-  for (uint32_t l = 0; l < L; l++) {
-    uint64_t idx = k * L + l;
-    if (idx < count) { G1Xyzz b = in[idx]; add(acc, b); }
-  }
-  out[k] = acc;
-}
-
 __global__ void k_set_inf(G1Xyzz* out, uint32_t count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) { G1Xyzz p; set_inf(p); out[i] = p; }
 }
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
-
-int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev) {
-  if (count == 0) {
-    k_set_inf<<<1, 32, 0, ctx->stream>>>(out_dev, 1);
-    KZG_LAUNCHED(ctx);
-    return KZG_OK;
-  }
-  void *a, *b;
-  uint64_t c1 = (count + 31) / 32;
-  KZG_TRY(scratch_get(ctx, SCR_RED_A, (c1 + 1) * sizeof(G1Xyzz), &a));
-  KZG_TRY(scratch_get(ctx, SCR_RED_B, ((c1 + 31) / 32 + 1) * sizeof(G1Xyzz), &b));
-  const G1Xyzz* src = in_dev;
-  G1Xyzz* bufs[2] = {reinterpret_cast<G1Xyzz*>(a), reinterpret_cast<G1Xyzz*>(b)};
-  int which = 0;
-  while (true) {
-    uint64_t chunks = (count + 31) / 32;
-    G1Xyzz* dst = chunks == 1 ? out_dev : bufs[which];
-    k_sum_warp<<<blocks_for(chunks * 32, 128), 128, 0, ctx->stream>>>(src, count, dst);
-    KZG_LAUNCHED(ctx);
-    if (chunks == 1) break;
-    src = dst; count = chunks; which ^= 1;
-  }
-  return KZG_OK;
-}
-
-// sum_b (b+1) * buckets[b] -> result_dev
-static int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* buckets, uint32_t M, G1Xyzz* result_dev) {
-  // level sizes M -> ceil(M/32) -> ... -> 1
-  uint32_t sizes[8]; int nlev = 0;
-  for (uint32_t m = M;; ) { uint32_t k = (m + 31) / 32; sizes[nlev++] = k; if (k == 1) break; m = k; }
-  size_t tot = 0;
-  for (int l = 0; l < nlev; l++) tot += sizes[l];
-  void* ws;
-  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, (2 * tot + 16) * sizeof(G1Xyzz), &ws));
-  G1Xyzz* W = reinterpret_cast<G1Xyzz*>(ws);
-  G1Xyzz* S = W + tot;
-  G1Xyzz* lvl = S + tot;
-  const G1Xyzz* cur = buckets;
-  uint32_t m = M; size_t off = 0;
-  const G1Xyzz* s_last = nullptr;
-  for (int l = 0; l < nlev; l++) {
-    k_reduce_warp<<<blocks_for((uint64_t)sizes[l] * 32, 128), 128, 0, ctx->stream>>>(cur, m, W + off, S + off);
-    KZG_LAUNCHED(ctx);
-    cur = S + off; s_last = S + off; m = sizes[l]; off += sizes[l];
-  }
-  off = 0;
-  for (int l = 0; l < nlev; l++) {
-    KZG_TRY(sum_points(ctx, W + off, sizes[l], lvl + l));
-    off += sizes[l];
-  }
-  k_reduce_final<<<1, 1, 0, ctx->stream>>>(lvl, nlev, s_last, result_dev);
-  KZG_LAUNCHED(ctx);
-  return KZG_OK;
-}
 
 int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
                    G1Xyzz* result_dev) {
@@ -370,9 +234,15 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   void* parts = bk;
   if (logT) KZG_TRY(scratch_get(ctx, SCR_PARTIALS, ((size_t)half << logT) * sizeof(G1Xyzz), &parts));
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  k_bucket_acc<<<blocks_for((uint64_t)half << logT, 128), 128, 0, ctx->stream>>>(
-      reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb), s->msm_tab, half, logT, heavy_cap,
-      reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
+  {
+    auto kern = k_bucket_acc<3>;
+    if (ctx->opt_acc_minblocks == 4) kern = k_bucket_acc<4>;
+    else if (ctx->opt_acc_minblocks == 5) kern = k_bucket_acc<5>;
+    else if (ctx->opt_acc_minblocks == 6) kern = k_bucket_acc<6>;
+    kern<<<blocks_for((uint64_t)half << logT, 128), 128, 0, ctx->stream>>>(
+        reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb), s->msm_tab, half, logT, heavy_cap,
+        reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
+  }
   KZG_LAUNCHED(ctx);
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   {
@@ -386,13 +256,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
                                              heavy_list, heavy_count);
     KZG_LAUNCHED(ctx);
   }
-  if (logT) {
-    k_sum_chunks<<<blocks_for(half, 128), 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(parts), (uint64_t)half << logT, T,
-                                                                 reinterpret_cast<G1Xyzz*>(bk));
-    KZG_LAUNCHED(ctx);
-  }
-
-  KZG_TRY(reduce_buckets(ctx, reinterpret_cast<G1Xyzz*>(bk), half, result_dev));
+  KZG_TRY(reduce_buckets(ctx, reinterpret_cast<G1Xyzz*>(parts), half, logT, result_dev));
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   return KZG_OK;
 }

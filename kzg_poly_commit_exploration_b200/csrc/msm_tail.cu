@@ -1,0 +1,278 @@
+// K2 tail — bucket reduction sum_b (b+1) * B_b and plain point sums (latency-bound part of the MSM).
+//
+// These kernels run a handful of warps through long chains of dependent XYZZ additions.  With the field
+// multiplication inlined an addition is ~84 KB of straight-line code executed ONCE per call, and a lone warp
+// then waits on instruction fetch, not on arithmetic (k_reduce_l3's single-thread Horner ran at 3.8 us per Fq
+// product against 1.4 us inside a resident loop).  This translation unit therefore compiles the Fq product
+// as a real function (KZG_FQ_NOINLINE: arguments in registers, one 6 KB copy), which keeps the whole tail
+// inside the instruction cache.
+#define KZG_FQ_NOINLINE 1
+#include "engine.cuh"
+
+namespace kzg {
+
+// ---- 5. reduce ---------------------------------------------------------------------------------
+// sum_i (i+1) * A_i over M buckets, warp-cooperatively.  A warp owns 32 consecutive buckets, one per
+// lane: a 5-step suffix scan through shuffles gives R_l = sum_{m>=l} A_m, hence S = R_0 and
+// W = sum_l l*A_l = sum_{l>=1} R_l (a 5-step tree).  Then sum_i i*A_i = sum_k W_k + 32 * sum_k k*S_k
+// and the second term is the same problem on the 32x smaller array S: log_32(M) levels of ten
+// sequential additions each instead of a 2L-long running sum per thread.
+__device__ __forceinline__ void shfl_down_pt(G1Xyzz& o, const G1Xyzz& p, int d) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    o.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
+    o.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
+    o.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], d);
+    o.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], d);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_reduce_warp(const G1Xyzz* __restrict__ A, uint32_t M, G1Xyzz* __restrict__ W_out, G1Xyzz* __restrict__ S_out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t chunks = (M + 31) >> 5;
+  if (k >= chunks) return;                       // whole warps exit together
+  const uint32_t idx = k * 32 + lane;
+  G1Xyzz R;
+  if (idx < M) R = A[idx]; else set_inf(R);
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {             // suffix scan
+    G1Xyzz o; shfl_down_pt(o, R, d);
+    if (lane + d < 32) add(R, o);
+  }
+  if (lane == 0) S_out[k] = R;
+  G1Xyzz X = R;
+  if (lane == 0) set_inf(X);
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {            // tree sum of R_1..R_31
+    G1Xyzz o; shfl_down_pt(o, X, d);
+    if (lane < d) add(X, o);
+  }
+  if (lane == 0) W_out[k] = X;
+}
+
+// out[k] = sum of in[32k .. 32k+32), one warp per output
+__global__ void __launch_bounds__(128)
+k_sum_warp(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t chunks = (count + 31) >> 5;
+  if (k >= chunks) return;
+  const uint64_t idx = k * 32 + lane;
+  G1Xyzz X;
+  if (idx < count) X = in[idx]; else set_inf(X);
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    G1Xyzz o; shfl_down_pt(o, X, d);
+    if (lane < d) add(X, o);
+  }
+  if (lane == 0) out[k] = X;
+}
+
+// result = S_total + Wsum_0 + 32*(Wsum_1 + 32*(Wsum_2 + ...)) : single thread, a handful of operations
+__global__ void k_reduce_final(const G1Xyzz* __restrict__ lvl, int nlevels, const G1Xyzz* __restrict__ s_total,
+                               G1Xyzz* __restrict__ out) {
+  G1Xyzz acc = lvl[nlevels - 1];
+  for (int l = nlevels - 2; l >= 0; l--) {
+    for (int k = 0; k < 5; k++) dbl(acc);
+    G1Xyzz w = lvl[l]; add(acc, w);
+  }
+  G1Xyzz st = s_total[0]; add(acc, st);
+  out[0] = acc;
+}
+
+// ---- fused tail (M <= 32768 buckets): three launches, ~47 dependent additions instead of ~71 -----------
+// The tail is latency-bound (a dependent XYZZ addition costs a lone warp ~15-20 us), so what matters is
+// the LENGTH of the dependency chain, not the work: independent chains run in different warps.
+__device__ __forceinline__ void warp_suffix_scan(G1Xyzz& R, uint32_t lane) {
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    G1Xyzz o; shfl_down_pt(o, R, d);
+    if (lane + d < 32) add(R, o);
+  }
+}
+__device__ __forceinline__ void warp_tree_sum(G1Xyzz& X, uint32_t lane) {
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    G1Xyzz o; shfl_down_pt(o, X, d);
+    if (lane < d) add(X, o);
+  }
+}
+
+// level 1: one warp owns 32 consecutive buckets, one per lane.  A lane first folds the T partials of its
+// bucket serially (every lane does useful work; a shuffle tree here would idle most lanes and, at 8x the
+// threads, no longer fit in one wave — measured 1.1 ms slower), then the warp turns the 32 bucket sums into
+// S_k = sum_l A_l and W_k = sum_l l*A_l (suffix scan + tree).  Blocks are single warps so that all
+// M/32 chains are resident at once: the tail is latency-bound.
+__global__ void __launch_bounds__(32)
+k_reduce_l1(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* __restrict__ W_out,
+            G1Xyzz* __restrict__ S_out) {
+  const uint32_t lane = threadIdx.x;
+  const uint32_t b = blockIdx.x * 32 + lane;
+  G1Xyzz X; set_inf(X);
+  if (b < M) {
+    X = parts[(size_t)b * T];
+#pragma unroll 1
+    for (uint32_t k = 1; k < T; k++) { G1Xyzz o = parts[(size_t)b * T + k]; add(X, o); }
+  }
+  warp_suffix_scan(X, lane);
+  if (lane == 0) S_out[blockIdx.x] = X;
+  if (lane == 0) set_inf(X);
+  warp_tree_sum(X, lane);
+  if (lane == 0) W_out[blockIdx.x] = X;
+}
+
+// level 2: chunk k of 32 level-1 outputs.  Even warps run the S chain (-> S1_k, W1_k), odd warps fold the
+// 32 W0 values of the same chunk (-> V_k), so the two chains overlap instead of queueing in one warp.
+__global__ void __launch_bounds__(128)
+k_reduce_l2(const G1Xyzz* __restrict__ S0, const G1Xyzz* __restrict__ W0, uint32_t m,
+            G1Xyzz* __restrict__ S1, G1Xyzz* __restrict__ W1, G1Xyzz* __restrict__ V) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t k = wid >> 1;
+  const uint32_t chunks = (m + 31) >> 5;
+  if (k >= chunks) return;
+  const uint32_t idx = k * 32 + lane;
+  G1Xyzz X;
+  if (wid & 1) {
+    if (idx < m) X = W0[idx]; else set_inf(X);
+    warp_tree_sum(X, lane);
+    if (lane == 0) V[k] = X;
+  } else {
+    if (idx < m) X = S0[idx]; else set_inf(X);
+    warp_suffix_scan(X, lane);
+    if (lane == 0) S1[k] = X;
+    if (lane == 0) set_inf(X);
+    warp_tree_sum(X, lane);
+    if (lane == 0) W1[k] = X;
+  }
+}
+
+// level 3 + Horner: m2 <= 32.  warp 0: S1 -> (S_total, W2); warp 1: sum W1; warp 2: sum V (= sum W0);
+// thread 0: out = S_total + sumW0 + 32*(sumW1 + 32*(W2 ...)), then the shallower pre-summed levels.
+__global__ void __launch_bounds__(96)
+k_reduce_l3(const G1Xyzz* __restrict__ S1, const G1Xyzz* __restrict__ W1, const G1Xyzz* __restrict__ V, uint32_t m2,
+            const G1Xyzz* __restrict__ pre, int npre, G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz sh[4];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  G1Xyzz X;
+  const G1Xyzz* src = w == 0 ? S1 : (w == 1 ? W1 : V);
+  if (lane < m2) X = src[lane]; else set_inf(X);
+  if (w == 0) {
+    warp_suffix_scan(X, lane);
+    if (lane == 0) sh[0] = X;          // S_total
+    if (lane == 0) set_inf(X);
+    warp_tree_sum(X, lane);            // W2
+  } else {
+    warp_tree_sum(X, lane);
+    if (lane == 0) sh[w] = X;          // sh[1] = sum W1, sh[2] = sum W0
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  G1Xyzz acc = X;                      // W2
+  for (int l = 1; l >= 0; l--) {
+    for (int k = 0; k < 5; k++) dbl(acc);
+    G1Xyzz t = sh[l == 1 ? 1 : 2]; add(acc, t);
+  }
+  for (int l = npre - 1; l >= 0; l--) {
+    for (int k = 0; k < 5; k++) dbl(acc);
+    G1Xyzz t = pre[l]; add(acc, t);
+  }
+  G1Xyzz st = sh[0]; add(acc, st);
+  out[0] = acc;
+}
+
+// out[k] = sum of in[k L .. k L + L)
+__global__ void __launch_bounds__(128)
+k_sum_chunks(const G1Xyzz* __restrict__ in, uint64_t count, uint32_t L, G1Xyzz* __restrict__ out) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t chunks = (count + L - 1) / L;
+  if (k >= chunks) return;
+  G1Xyzz acc; set_inf(acc);
+#pragma unroll 1
+  for (uint32_t l = 0; l < L; l++) {
+    uint64_t idx = k * L + l;
+    if (idx < count) { G1Xyzz b = in[idx]; add(acc, b); }
+  }
+  out[k] = acc;
+}
+
+__global__ void k_set_inf_tail(G1Xyzz* out, uint32_t count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) { G1Xyzz p; set_inf(p); out[i] = p; }
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev) {
+  if (count == 0) {
+    k_set_inf_tail<<<1, 32, 0, ctx->stream>>>(out_dev, 1);
+    KZG_LAUNCHED(ctx);
+    return KZG_OK;
+  }
+  void *a, *b;
+  uint64_t c1 = (count + 31) / 32;
+  KZG_TRY(scratch_get(ctx, SCR_RED_A, (c1 + 1) * sizeof(G1Xyzz), &a));
+  KZG_TRY(scratch_get(ctx, SCR_RED_B, ((c1 + 31) / 32 + 1) * sizeof(G1Xyzz), &b));
+  const G1Xyzz* src = in_dev;
+  G1Xyzz* bufs[2] = {reinterpret_cast<G1Xyzz*>(a), reinterpret_cast<G1Xyzz*>(b)};
+  int which = 0;
+  while (true) {
+    uint64_t chunks = (count + 31) / 32;
+    G1Xyzz* dst = chunks == 1 ? out_dev : bufs[which];
+    k_sum_warp<<<blocks_for(chunks * 32, 128), 128, 0, ctx->stream>>>(src, count, dst);
+    KZG_LAUNCHED(ctx);
+    if (chunks == 1) break;
+    src = dst; count = chunks; which ^= 1;
+  }
+  return KZG_OK;
+}
+
+// sum_b (b+1) * A_b -> result_dev, where A_b = sum_k parts[b*T + k], T = 2^logT partials per bucket
+int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, G1Xyzz* result_dev) {
+  // shallow levels (only for M > 32768, i.e. windows wider than 16 bits) run one launch per step and leave
+  // their W sums in pre[]; the last three levels are the fused tail.
+  void* ws;
+  uint32_t shallow = 0;
+  for (uint32_t m = M; m > 32768; m = (m + 31) / 32) shallow++;
+  size_t cap = (size_t)(M + 31) / 32 * 2 * 2 + 4096;
+  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, cap * sizeof(G1Xyzz), &ws));
+  G1Xyzz* pool = reinterpret_cast<G1Xyzz*>(ws);
+  G1Xyzz* pre = pool; pool += 8;
+  const G1Xyzz* cur = parts;
+  uint32_t m = M;
+  if (shallow) {
+    if (logT) {          // fold the T partials first: the generic level kernel takes one value per bucket
+      void* bk;
+      KZG_TRY(scratch_get(ctx, SCR_BUCKETS, (size_t)M * sizeof(G1Xyzz), &bk));
+      k_sum_chunks<<<blocks_for(M, 128), 128, 0, ctx->stream>>>(parts, (uint64_t)M << logT, 1u << logT,
+                                                                reinterpret_cast<G1Xyzz*>(bk));
+      KZG_LAUNCHED(ctx);
+      cur = reinterpret_cast<G1Xyzz*>(bk); logT = 0;
+    }
+    for (uint32_t l = 0; l < shallow; l++) {
+      uint32_t k = (m + 31) / 32;
+      G1Xyzz* W = pool; pool += k;
+      G1Xyzz* S = pool; pool += k;
+      k_reduce_warp<<<blocks_for((uint64_t)k * 32, 128), 128, 0, ctx->stream>>>(cur, m, W, S);
+      KZG_LAUNCHED(ctx);
+      KZG_TRY(sum_points(ctx, W, k, pre + l));
+      cur = S; m = k;
+    }
+  }
+  const uint32_t m1 = (m + 31) / 32, m2 = (m1 + 31) / 32;
+  G1Xyzz* S0 = pool; pool += m1;
+  G1Xyzz* W0 = pool; pool += m1;
+  G1Xyzz* S1 = pool; pool += m2;
+  G1Xyzz* W1 = pool; pool += m2;
+  G1Xyzz* V = pool; pool += m2;
+  k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
+  k_reduce_l2<<<blocks_for((uint64_t)m2 * 64, 128), 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V);
+  KZG_LAUNCHED(ctx);
+  k_reduce_l3<<<1, 96, 0, ctx->stream>>>(S1, W1, V, m2, pre, (int)shallow, result_dev);
+  KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
+}  // namespace kzg

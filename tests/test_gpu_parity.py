@@ -249,7 +249,7 @@ def test_commit_adversarial_scalars(ctx, setup8k, kind):
     assert got == O.g1_compress(O.commit_known_secret(ints, S))
 
 
-@pytest.mark.parametrize("c", [4, 7, 11, 13, 16])
+@pytest.mark.parametrize("c", [4, 7, 11, 13, 16, 17, 19])
 def test_msm_window_sizes(ctx, c):
     st = ctx.setup_generate(SECRET, 2000)
     st.prepare_msm(c)
@@ -261,6 +261,13 @@ def test_msm_window_sizes(ctx, c):
         assert ctx.msm_g1(st, scal) == O.g1_compress(O.commit_known_secret(util.to_ints(scal), S))
     finally:
         ctx.set_option("heavy_cap", 1024)
+    # every threads-per-bucket split of the accumulate kernel / fused tail (T = 1 .. 32)
+    for split in (0, 1, 2, 3, 5):
+        ctx.set_option("acc_split", split)
+        try:
+            assert ctx.msm_g1(st, scal) == O.g1_compress(O.commit_known_secret(util.to_ints(scal), S)), split
+        finally:
+            ctx.set_option("acc_split", -1)
     st.close()
 
 

@@ -1,0 +1,23 @@
+"""Tuning sweep for the accumulate kernel (not a benchmark): acc_minblocks x acc_split at n = 2^20."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import kzg_oracle as O
+import util
+import kzg_poly_commit_exploration_b200 as pkg
+
+n = 1 << 20
+ctx = pkg.Context(0)
+st = ctx.setup_generate(O.BENCH_SECRET_BE, n)
+st.prepare_msm(16)
+scal = util.scalar_stream_bytes(0xC3, n)
+exp = O.g1_compress(O.commit_known_secret(util.to_ints(scal), O.fr_from_be_bytes(O.BENCH_SECRET_BE)))
+for mb in (3, 4, 5, 6):
+    for sp in (2, 3, 4):
+        ctx.set_option("acc_minblocks", mb); ctx.set_option("acc_split", sp)
+        best = None
+        for rep in range(4):
+            got = ctx.msm_g1(st, scal)
+            r = (ctx.last_kernel_ms(0), ctx.last_kernel_ms(1), got == exp)
+            if rep and (best is None or r[0] < best[0]): best = r
+        print(f"minblocks={mb} split={sp}: acc {best[0]:.3f} ms  total-dev {best[1]:.3f} ms ok={best[2]}", flush=True)
