@@ -12,13 +12,9 @@
 //   4. accumulate: one thread per bucket, XYZZ += affine (8M+2S), table points fetched with
 //                 128-bit loads; buckets above `heavy_cap` entries (adversarial inputs: all-equal
 //                 scalars) go to a block-per-bucket kernel with a shared-memory tree.
-//   5. reduce   : sum_b (b+1) * B_b, chunked: a thread owns L buckets, forms the running-sum
-//                 W_k and S_k, adds (k L) * S_k by a short double-and-add, then a tree sum.
+//   5. reduce   : sum_b (b+1) * B_b by warp-level suffix scans, three fused launches (msm_tail.cu).
 // Integer-multiply bound: 3 000 wide multiply-adds per bucket addition, 96 B of HBM per addition.
 #include <cub/device/device_radix_sort.cuh>
-#ifdef KZG_ACC_NOINLINE
-#define KZG_FQ_NOINLINE 1
-#endif
 #include "engine.cuh"
 
 namespace kzg {
