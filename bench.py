@@ -94,7 +94,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 1024 * threads
+    sample = 8192 * threads
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_ref
     from kzg_poly_commit_exploration_b200 import synthetic
@@ -239,7 +239,8 @@ def run_ours(args):
         achieved = adds * MAC_PER_BUCKET_ADD / (acc * 1e-3)
         hbm_bytes = adds * 100  # 96 B affine point + 4 B sorted index per bucket addition
         threads = os.cpu_count() or 1
-        cpu_val, cpu_dt = cpu_baseline(1024 * threads, threads) if world == 1 else (None, None)
+        cpu_points = min(1 << LOG_N, 49152 * threads)   # ~10 s of host work
+        cpu_val, cpu_dt = cpu_baseline(cpu_points, threads) if world == 1 else (None, None)
         line = {
             "metric": "kzg_commit_msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -269,7 +270,7 @@ def run_ours(args):
             line["blob_batch"] = blob
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": "points/s", "cores": threads, "kind": "port",
-                                    "sample": f"{1024 * threads}-point prefix of the same scalars, reference naive loop "
+                                    "sample": f"{cpu_points}-point prefix of the same scalars, reference naive loop "
                                               f"(src/polynomial.rs:207-212) split over {threads} threads, {cpu_dt:.2f} s"}
         print(json.dumps(line))
     if blob is None:
@@ -358,7 +359,7 @@ def main():
     ap.add_argument("--window", type=int, default=int(os.environ.get("KZG_WINDOW", "0")))
     ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BLOBS", "4096")),
                     help="size of the secondary blob batch (0 = skip)")
-    ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "10")))
+    ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "13")))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
