@@ -80,6 +80,15 @@ int32_t kzg_setup_import_g1(kzg_ctx* ctx, const uint8_t* g1_c48, uint64_t n, kzg
 int32_t kzg_setup_export_g1(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count,
                             uint8_t* out_c48);
 uint64_t kzg_setup_len(const kzg_setup* s);
+/* G2 half of SetupArtifact (src/trusted_setup.rs:31-35, 64-72): [s^i]G2 for items 0..count of the setup
+ * (count <= len; the reference carries one per item, verify_proof reads only item 1), kept on the device
+ * as 96-byte compressed points = Serialize for G2Point (src/curves.rs:260-271). */
+int32_t kzg_setup_generate_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t secret_be[32], uint64_t count);
+/* Deserialize for G2Point x count (src/curves.rs:273-343): on-curve check, no subgroup check */
+int32_t kzg_setup_import_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t* g2_c96, uint64_t count);
+int32_t kzg_setup_export_g2(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count,
+                            uint8_t* out_c96);
+uint64_t kzg_setup_g2_len(const kzg_setup* s);
 void kzg_setup_destroy(kzg_setup* s);
 /* Precompute per-base tables once per setup (amortised over every later commit):
  *   kzg_setup_prepare_msm  : 2^(c*j) * P_i for all windows j (folds every Pippenger window
@@ -152,6 +161,20 @@ int32_t kzg_g1_mul(const uint8_t p[48], const uint8_t k_le[32], uint8_t out[48])
 void kzg_g1_from_scalar(const uint8_t k_le[32], uint8_t out[48]);
 /* on-curve / encoding check of one compressed point: KZG_OK or KZG_E_BAD_POINT */
 int32_t kzg_g1_check(const uint8_t p[48]);
+/* G2Point::{from_scalar, sub} (src/curves.rs:225-249) + add / neg on 96-byte compressed points */
+void kzg_g2_from_scalar(const uint8_t k_le[32], uint8_t out[96]);
+int32_t kzg_g2_add(const uint8_t a[96], const uint8_t b[96], uint8_t out[96]);
+int32_t kzg_g2_sub(const uint8_t a[96], const uint8_t b[96], uint8_t out[96]);
+int32_t kzg_g2_neg(const uint8_t a[96], uint8_t out[96]);
+int32_t kzg_g2_check(const uint8_t p[96]);
+/* bilinear_map(a1, b1) == bilinear_map(a2, b2) (src/curves.rs:355-371; only equality is ever consumed,
+ * src/polynomial.rs:293): one product of Miller loops + one final exponentiation, host code */
+int32_t kzg_pairing_equal(const uint8_t a1[48], const uint8_t b1[96], const uint8_t a2[48],
+                          const uint8_t b2[96], int32_t* equal);
+/* Evaluation::verify_proof (src/polynomial.rs:276-294): e(proof, [s]_2 - [z]_2) == e(C - [y]_1, [1]_2);
+ * g2_tau = setup[1].g2.  *ok receives 1 / 0. */
+int32_t kzg_verify_proof(const uint8_t proof[48], const uint8_t commitment[48], const uint8_t z_le[32],
+                         const uint8_t y_le[32], const uint8_t g2_tau[96], int32_t* ok);
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
 /* integer-pipe roofline probe: independent 32x32+64 multiply-add chains on every SM;

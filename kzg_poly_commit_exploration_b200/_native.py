@@ -36,6 +36,10 @@ SIGNATURES = {
     "kzg_setup_import_g1": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "kzg_setup_export_g1": (_i32, [_vp, _vp, _u64, _u64, _vp]),
     "kzg_setup_len": (_u64, [_vp]),
+    "kzg_setup_generate_g2": (_i32, [_vp, _vp, _vp, _u64]),
+    "kzg_setup_import_g2": (_i32, [_vp, _vp, _vp, _u64]),
+    "kzg_setup_export_g2": (_i32, [_vp, _vp, _u64, _u64, _vp]),
+    "kzg_setup_g2_len": (_u64, [_vp]),
     "kzg_setup_destroy": (None, [_vp]),
     "kzg_setup_prepare_msm": (_i32, [_vp, _vp, _i32]),
     "kzg_setup_prepare_fixed": (_i32, [_vp, _vp, _u64, _i32]),
@@ -63,6 +67,13 @@ SIGNATURES = {
     "kzg_g1_mul": (_i32, [_vp, _vp, _vp]),
     "kzg_g1_from_scalar": (None, [_vp, _vp]),
     "kzg_g1_check": (_i32, [_vp]),
+    "kzg_g2_from_scalar": (None, [_vp, _vp]),
+    "kzg_g2_add": (_i32, [_vp, _vp, _vp]),
+    "kzg_g2_sub": (_i32, [_vp, _vp, _vp]),
+    "kzg_g2_neg": (_i32, [_vp, _vp]),
+    "kzg_g2_check": (_i32, [_vp]),
+    "kzg_pairing_equal": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(_i32)]),
+    "kzg_verify_proof": (_i32, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i32)]),
     "kzg_probe_imad_peak": (_i32, [_vp, C.POINTER(C.c_double)]),
     "kzg_probe_fq_mul": (_i32, [_vp, C.POINTER(C.c_double)]),
     "kzg_selftest_fq_mul": (_i32, [_vp, _vp, _vp, _u64, _vp]),

@@ -128,6 +128,7 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
   for (int i = 0; i < SCR_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->gtable) cudaFree(ctx->gtable);
+  if (ctx->g2table) cudaFree(ctx->g2table);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; i++) if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -192,6 +193,7 @@ int32_t kzg_setup_generate(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t f
   DeviceGuard g(ctx->device);
   kzg_setup* s = nullptr;
   KZG_TRY(setup_alloc(ctx, n, &s));
+  s->first = first;
   int32_t st = setup_generate_dev(ctx, secret_be, first, n, s->bases);
   if (st == KZG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, KZG_E_CUDA, "sync after setup generation");
   if (st != KZG_OK) { kzg_setup_destroy(s); return st; }
@@ -236,6 +238,56 @@ int32_t kzg_setup_export_g1(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, ui
 
 uint64_t kzg_setup_len(const kzg_setup* s) { return s ? s->n : 0; }
 
+// ---- G2 half of SetupArtifact (src/trusted_setup.rs:31-35, 64-72) ----------------------------
+static int32_t setup_g2_alloc(kzg_ctx* ctx, kzg_setup* s, uint64_t count) {
+  if (s->g2_c96) { cudaFree(s->g2_c96); s->g2_c96 = nullptr; s->g2_n = 0; }
+  if (count == 0) return KZG_OK;
+  if (cudaMalloc(&s->g2_c96, count * 96) != cudaSuccess) { cudaGetLastError(); return fail(ctx, KZG_E_NOMEM, "cudaMalloc(g2)"); }
+  s->g2_n = count;
+  return KZG_OK;
+}
+
+int32_t kzg_setup_generate_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t secret_be[32], uint64_t count) {
+  if (!ctx || !s || !secret_be) return KZG_E_BAD_ARG;
+  if (count > s->n) return fail(ctx, KZG_E_BAD_ARG, "more G2 items than setup items");
+  DeviceGuard g(ctx->device);
+  KZG_TRY(setup_g2_alloc(ctx, s, count));
+  KZG_TRY(setup_generate_g2_dev(ctx, secret_be, s->first, count, s->g2_c96));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return KZG_OK;
+}
+
+int32_t kzg_setup_import_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t* g2_c96, uint64_t count) {
+  if (!ctx || !s || (!g2_c96 && count)) return KZG_E_BAD_ARG;
+  if (count > s->n) return fail(ctx, KZG_E_BAD_ARG, "more G2 items than setup items");
+  // Deserialize for G2Point (src/curves.rs:273-343): length fixed by the ABI, blst_p2_uncompress semantics
+  // (flags, coordinates < q, on-curve; no subgroup check) — validated on the host, point by point
+  for (uint64_t i = 0; i < count; i++) {
+    if (kzg_g2_check(g2_c96 + 96 * i) != KZG_OK) {
+      ctx->err = "Got error while uncompressing: G2 point " + std::to_string(i);
+      return KZG_E_BAD_POINT;
+    }
+  }
+  DeviceGuard g(ctx->device);
+  KZG_TRY(setup_g2_alloc(ctx, s, count));
+  if (count) {
+    KZG_CUDA_OK(ctx, cudaMemcpyAsync(s->g2_c96, g2_c96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return KZG_OK;
+}
+
+int32_t kzg_setup_export_g2(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count, uint8_t* out_c96) {
+  if (!ctx || !s || first + count > s->g2_n) return fail(ctx, KZG_E_BAD_ARG, "export range outside the G2 items");
+  if (count == 0) return KZG_OK;
+  DeviceGuard g(ctx->device);
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c96, s->g2_c96 + first * 96, count * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return KZG_OK;
+}
+
+uint64_t kzg_setup_g2_len(const kzg_setup* s) { return s ? s->g2_n : 0; }
+
 void kzg_setup_destroy(kzg_setup* s) {
   if (!s) return;
   DeviceGuard g(s->ctx->device);
@@ -243,6 +295,7 @@ void kzg_setup_destroy(kzg_setup* s) {
   if (s->bases) cudaFree(s->bases);
   if (s->msm_tab) cudaFree(s->msm_tab);
   if (s->fix_tab) cudaFree(s->fix_tab);
+  if (s->g2_c96) cudaFree(s->g2_c96);
   delete s;
 }
 

@@ -34,6 +34,7 @@ struct kzg_ctx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   kzg::G1Affine* gtable = nullptr;     // [16][32768] multiples of the generator (setup generation)
+  void* g2table = nullptr;             // [32][255] multiples of the G2 generator (setup_g2.cu)
   int opt_msm_window = 0;              // 0 = auto
   int opt_fixed_window = 0;            // 0 = auto
   int opt_reduce_chunk = 16;
@@ -46,7 +47,10 @@ struct kzg_ctx {
 struct kzg_setup {
   kzg_ctx* ctx = nullptr;
   uint64_t n = 0;
+  uint64_t first = 0;                  // index of bases[0] in the powers-of-tau sequence (range sharding)
   kzg::G1Affine* bases = nullptr;      // [n] affine Montgomery, (0,0) = infinity
+  uint8_t* g2_c96 = nullptr;           // [g2_n] compressed G2 powers (device), items 0..g2_n of this setup
+  uint64_t g2_n = 0;
   // folded-window table for the bucket MSM: tab[j*n + i] = 2^(c*j) * P_i ; tab window 0 == bases
   int msm_c = 0, msm_w = 0;
   kzg::G1Affine* msm_tab = nullptr;    // [(w) * n]  (window 0 aliases nothing: full copy kept for simple indexing)
@@ -108,6 +112,11 @@ int32_t compress_points(kzg_ctx* ctx, const G1Affine* in_dev, uint64_t n, uint8_
 int32_t uncompress_points(kzg_ctx* ctx, const uint8_t* in_dev, uint64_t n, G1Affine* out_dev, int* bad_index);
 int32_t build_msm_table(kzg_ctx* ctx, kzg_setup* s, int c);
 int32_t build_fixed_table(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int c);
+
+// ---- setup_g2.cu (K3') ---------------------------------------------------------------------
+// [s^(first+i)]G2, i < n, as 96-byte compressed points (device)
+int32_t setup_generate_g2_dev(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t first, uint64_t n,
+                              uint8_t* out_c96_dev);
 
 // ---- msm.cu (K2) -----------------------------------------------------------------------------
 // result_dev: one G1Xyzz (device).  Uses s->msm_tab (built on demand).

@@ -176,6 +176,25 @@ class Setup:
         self.ctx.check(N.lib().kzg_setup_export_g1(self.ctx._h, self._h, first, count, o))
         return bytes(o)[: count * 48]
 
+    def generate_g2(self, secret_be: bytes, count: int | None = None):
+        """[s^i]G2 for items 0..count of this setup (src/trusted_setup.rs:64-72), kept on the device."""
+        count = len(self) if count is None else count
+        self.ctx.check(N.lib().kzg_setup_generate_g2(self.ctx._h, self._h, _ptr(secret_be), count))
+
+    def import_g2(self, g2_c96: bytes):
+        if len(g2_c96) % 96:
+            raise N.KzgNativeError(5, f"Invalid length, expected a multiple of 96, got {len(g2_c96)}")
+        self.ctx.check(N.lib().kzg_setup_import_g2(self.ctx._h, self._h, _ptr(g2_c96), len(g2_c96) // 96))
+
+    def g2_len(self) -> int:
+        return int(N.lib().kzg_setup_g2_len(self._h))
+
+    def export_g2(self, first: int = 0, count: int | None = None) -> bytes:
+        count = self.g2_len() - first if count is None else count
+        o = N.out(max(count, 1) * 96)
+        self.ctx.check(N.lib().kzg_setup_export_g2(self.ctx._h, self._h, first, count, o))
+        return bytes(o)[: count * 96]
+
     def prepare_msm(self, window_bits: int = 0):
         self.ctx.check(N.lib().kzg_setup_prepare_msm(self.ctx._h, self._h, window_bits))
 

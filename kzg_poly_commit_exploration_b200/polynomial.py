@@ -5,7 +5,7 @@ call into the CUDA engine (kzg_commit / kzg_evaluate / kzg_quotient / kzg_open).
 from __future__ import annotations
 
 from . import _native as N
-from .curves import G1Point
+from .curves import G1Point, G2Point, bilinear_maps_equal
 from .scalar import Scalar
 from .trusted_setup import TrustedSetup
 
@@ -122,6 +122,16 @@ class Evaluation:
         except N.KzgNativeError as e:
             raise _wrap(e) from None
         return G1Point._raw(proof)
+
+    def verify_proof(self, proof: G1Point, commitment: G1Point, setup_artifacts) -> bool:
+        """src/polynomial.rs:276-294: e(proof, setup[1].g2 - [point]_2) == e(commitment - [result]_1, [1]_2).
+        Indexing setup[1] fails on a setup shorter than 2 items, as the reference's does (:284)."""
+        tau2 = setup_artifacts[1].g2
+        if tau2 is None:
+            raise KzgError("SETUP_TOO_SHORT", "setup item 1 carries no G2 point")
+        lhs_g2 = tau2.sub(G2Point.from_scalar(self.point))
+        rhs_g1 = commitment.sub(G1Point.from_scalar(self.result))
+        return bilinear_maps_equal(proof, lhs_g2, rhs_g1, G2Point.from_i128(1))
 
     def to_json(self):
         return {"point": self.point.to_json(), "result": self.result.to_json()}

@@ -227,6 +227,46 @@ def test_commit_matches_reference_loop(ctx):
     st.close()
 
 
+# ---- G2 half of SetupArtifact (src/trusted_setup.rs:64-72) ----------------------------------------------
+def test_setup_g2_kat_and_known_secret(ctx):
+    n = 300
+    st = ctx.setup_generate(SECRET, n)
+    st.generate_g2(SECRET, n)
+    g2 = st.export_g2()
+    assert len(g2) == 96 * n and st.g2_len() == n
+    assert g2[:96] == O.g2_compress(O.G2)                                    # item 0 = generator whatever s is
+    # SURVEY §8c known-answer vector for setup[1].g2 with the bench secret
+    assert g2[96:192].hex() == ("a7290fc800d2d14f2dc5e5cb416bebf3267dfed1c6c3a79c6edc4ebd1e657d956daa06a2fcaafd42c94b65b32d4d43ea"
+                                "1368f861006829c475b7d54763a502dfd717e9d51c5cc7deae2981e56090a821c9c5bcafc129b8599203ab99031f4ce7")
+    for i in (1, 2, 3, 17, 255, 256, n - 1):
+        assert g2[96 * i: 96 * i + 96] == O.g2_compress(O.g2_from_scalar(pow(S, i, O.R))), i
+    # range sharding: a setup starting at item 1000 carries [s^(1000+i)]G2
+    sh = ctx.setup_generate(SECRET, 8, first=1000)
+    sh.generate_g2(SECRET, 4)
+    assert sh.export_g2(3, 1) == O.g2_compress(O.g2_from_scalar(pow(S, 1003, O.R)))
+    # import: round trip and rejection of a malformed point
+    imp = ctx.setup_import_g1(st.export_g1(0, 4))
+    imp.import_g2(g2[: 96 * 4])
+    assert imp.export_g2() == g2[: 96 * 4]
+    bad = bytearray(g2[: 96 * 2]); bad[96] &= 0x7F
+    with pytest.raises(Exception) as ei:
+        imp.import_g2(bytes(bad))
+    assert "uncompress" in str(ei.value)
+    for h in (st, sh, imp):
+        h.close()
+
+
+@pytest.mark.parametrize("secret_int", [0, 1, O.R - 1])
+def test_setup_g2_degenerate_secrets(ctx, secret_int):
+    sec = secret_int.to_bytes(32, "big")
+    st = ctx.setup_generate(sec, 5)
+    st.generate_g2(sec, 5)
+    g2 = st.export_g2()
+    for i in range(5):
+        assert g2[96 * i: 96 * i + 96] == O.g2_compress(O.g2_from_scalar(pow(secret_int, i, O.R))), i
+    st.close()
+
+
 # ---- adversarial scalar sets (bucket collisions, heavy buckets, cancellations) ----------------------
 @pytest.mark.parametrize("kind", ["zeros", "ones", "equal", "rminus1", "small", "alternating"])
 def test_commit_adversarial_scalars(ctx, setup8k, kind):

@@ -6,7 +6,7 @@ import random
 import pytest
 
 import kzg_oracle as O
-from kzg_poly_commit_exploration_b200.curves import G1Point
+from kzg_poly_commit_exploration_b200.curves import G1Point, G2Point, bilinear_maps_equal
 from kzg_poly_commit_exploration_b200.polynomial import Evaluation, KzgError, Polynomial
 from kzg_poly_commit_exploration_b200.scalar import Scalar
 
@@ -55,6 +55,21 @@ def test_compression_and_serialization_roundtrip():
         G1Point(bytes(48))
 
 
+def test_g2_point_mirror():
+    g = G2Point.from_i128(1)
+    assert g.compress() == O.g2_compress(O.G2)
+    assert G2Point.from_i128(-3).compress() == O.g2_compress(O.g2_neg(O.g2_mul(O.G2, 3)))
+    assert G2Point.from_scalar(Scalar.from_i128(5)).sub(G2Point.from_i128(2)) == G2Point.from_i128(3)
+    assert G2Point.from_json(g.to_json()) == g
+    with pytest.raises(Exception):
+        G2Point(bytes(96))
+    with pytest.raises(Exception):
+        G2Point(bytes(95))
+    a, b = Scalar.from_i128(77), Scalar.from_i128(1001)
+    assert bilinear_maps_equal(G1Point.from_scalar(a), G2Point.from_scalar(b),
+                               G1Point.from_scalar(a.mul(b)), G2Point.from_i128(1))
+
+
 # ---- src/polynomial.rs:301-321 -----------------------------------------------------------------------
 def test_create_polynomial_with_tailing_zeros():
     p = Polynomial.try_from([1, 2, 3, 0, 0])
@@ -75,7 +90,10 @@ def _kate_roundtrip(ctx, secret, coeffs_i128, point_i128):
     commitment = poly.commit(setup)
     evaluation = poly.evaluate(x, ctx)
     proof = evaluation.generate_proof(poly, setup)
-    # the pairing check stays with the CPU oracle (blst in a Rust integration): e(pi,[s-z]2) == e(C-[y]1,G2)
+    # Evaluation::verify_proof through the library's own pairing (src/lib.rs:26-32) ...
+    assert evaluation.verify_proof(proof, commitment, setup)
+    assert not Evaluation(x, evaluation.result.add(Scalar.from_i128(1))).verify_proof(proof, commitment, setup)
+    # ... and, independently, through the oracle's pairing: e(pi,[s-z]2) == e(C-[y]1,G2)
     so = O.setup_generate(secret, max(2, poly.degree() + 1))
     ev = O.Evaluation(int(x), int(evaluation.result))
     assert ev.verify_proof(O.g1_uncompress(proof.compress()), O.g1_uncompress(commitment.compress()), so)
