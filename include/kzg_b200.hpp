@@ -3,11 +3,12 @@
 // The reference is compiled code (Rust); with no Rust toolchain in this image the host side above the
 // C ABI is C++ with the SAME module / type / method names and error messages:
 //   scalar::Scalar                    src/scalar.rs
-//   curves::G1Point                   src/curves.rs:10-183
+//   curves::{G1Point, G2Point, bilinear_maps_equal}   src/curves.rs
 //   trusted_setup::{SetupArtifactsGenerator, SetupArtifact, TrustedSetup}   src/trusted_setup.rs
 //   polynomial::{Polynomial, Evaluation}                                    src/polynomial.rs
 // anyhow::Error becomes kzg::Error (what() carries the reference's message).  One FFI call per bulk op.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <memory>
@@ -69,6 +70,18 @@ class Scalar {
   bool is_zero() const { for (auto b : le_) if (b) return false; return true; }
   bool operator==(const Scalar& o) const { return le_ == o.le_; }
   bool operator!=(const Scalar& o) const { return !(*this == o); }
+  // impl Display: base-10 string of the canonical value (src/scalar.rs:272-345)
+  std::string to_string() const {
+    std::array<uint8_t, 32> q = le_;
+    std::string digits;
+    bool nonzero = true;
+    while (nonzero) {
+      unsigned rem = 0; nonzero = false;
+      for (int i = 31; i >= 0; i--) { unsigned cur = (rem << 8) | q[i]; q[i] = (uint8_t)(cur / 10); rem = cur % 10; if (q[i]) nonzero = true; }
+      digits.push_back((char)('0' + rem));
+    }
+    return std::string(digits.rbegin(), digits.rend());
+  }
  private:
   std::array<uint8_t, 32> le_;
 };
@@ -97,10 +110,41 @@ class G1Point {
  private:
   std::array<uint8_t, 48> c_{};
 };
+
+// src/curves.rs:185-343
+class G2Point {
+ public:
+  static G2Point from_compressed(const uint8_t* b, size_t len) {
+    if (len != 96) throw Error(KZG_E_BAD_LENGTH, "Invalid length, expected 96, got " + std::to_string(len));
+    if (kzg_g2_check(b) != KZG_OK) throw Error(KZG_E_BAD_POINT, "Got error while uncompressing");
+    G2Point p; std::copy(b, b + 96, p.c_.begin()); return p;
+  }
+  static G2Point from_scalar(const scalar::Scalar& a) { G2Point p; kzg_g2_from_scalar(a.to_le_bytes().data(), p.c_.data()); return p; }
+  static G2Point from_i128(__int128 a) {
+    G2Point p = from_scalar(scalar::Scalar::from_i128(a < 0 ? -a : a));
+    if (a < 0) { G2Point n; kzg_g2_neg(p.c_.data(), n.c_.data()); return n; }
+    return p;
+  }
+  G2Point sub(const G2Point& b) const { G2Point r; kzg_g2_sub(c_.data(), b.c_.data(), r.c_.data()); return r; }
+  const std::array<uint8_t, 96>& compressed() const { return c_; }   // Serialize (src/curves.rs:260-271)
+  bool operator==(const G2Point& o) const { return c_ == o.c_; }
+  static G2Point raw(const uint8_t* b) { G2Point p; std::copy(b, b + 96, p.c_.begin()); return p; }
+ private:
+  std::array<uint8_t, 96> c_{};
+};
+
+// bilinear_map(p1, q1) == bilinear_map(p2, q2) (src/curves.rs:355-371; the only use of the pairing,
+// src/polynomial.rs:293)
+inline bool bilinear_maps_equal(const G1Point& p1, const G2Point& q1, const G1Point& p2, const G2Point& q2) {
+  int32_t eq = 0;
+  int32_t st = kzg_pairing_equal(p1.compressed().data(), q1.compressed().data(), p2.compressed().data(), q2.compressed().data(), &eq);
+  if (st != KZG_OK) throw Error(st, kzg_status_string(st));
+  return eq != 0;
+}
 }  // namespace curves
 
 namespace trusted_setup {
-struct SetupArtifact { curves::G1Point g1; };
+struct SetupArtifact { curves::G1Point g1; curves::G2Point g2; bool has_g2 = false; };
 
 // Vec<SetupArtifact> + its device-resident copy
 class TrustedSetup {
@@ -109,9 +153,24 @@ class TrustedSetup {
   ~TrustedSetup() { kzg_setup_destroy(h_); }
   TrustedSetup(const TrustedSetup&) = delete;
   size_t len() const { return kzg_setup_len(h_); }
+  size_t g2_len() const { return kzg_setup_g2_len(h_); }
   SetupArtifact at(size_t i) const {
+    if (i >= len()) throw std::out_of_range("index out of bounds: the len is " + std::to_string(len()) + " but the index is " + std::to_string(i));
     uint8_t b[48]; ctx_->check(kzg_setup_export_g1(ctx_->get(), h_, i, 1, b));
-    return SetupArtifact{curves::G1Point::raw(b)};
+    SetupArtifact a; a.g1 = curves::G1Point::raw(b);
+    if (i < g2_len()) { uint8_t c[96]; ctx_->check(kzg_setup_export_g2(ctx_->get(), h_, i, 1, c)); a.g2 = curves::G2Point::raw(c); a.has_g2 = true; }
+    return a;
+  }
+  // Vec<SetupArtifact> from deserialised artifacts (the CLI's setup.json path)
+  static std::unique_ptr<TrustedSetup> from_artifacts(std::shared_ptr<Context> ctx, const std::vector<SetupArtifact>& items) {
+    std::vector<uint8_t> g1(items.size() * 48), g2;
+    for (size_t i = 0; i < items.size(); i++) std::copy(items[i].g1.compressed().begin(), items[i].g1.compressed().end(), g1.begin() + 48 * i);
+    for (size_t i = 0; i < items.size() && items[i].has_g2; i++) g2.insert(g2.end(), items[i].g2.compressed().begin(), items[i].g2.compressed().end());
+    kzg_setup* h = nullptr;
+    ctx->check(kzg_setup_import_g1(ctx->get(), g1.data(), items.size(), &h));
+    auto out = std::make_unique<TrustedSetup>(ctx, h);
+    if (!g2.empty()) ctx->check(kzg_setup_import_g2(ctx->get(), h, g2.data(), g2.size() / 96));
+    return out;
   }
   void prepare_msm(int window_bits = 0) { ctx_->check(kzg_setup_prepare_msm(ctx_->get(), h_, window_bits)); }
   void prepare_fixed(size_t n_points, int window_bits = 0) { ctx_->check(kzg_setup_prepare_fixed(ctx_->get(), h_, n_points, window_bits)); }
@@ -126,10 +185,13 @@ class SetupArtifactsGenerator {
  public:
   SetupArtifactsGenerator(std::shared_ptr<Context> ctx, const std::array<uint8_t, 32>& secret_be) : ctx_(std::move(ctx)), secret_(secret_be) {}
   // .take(n).collect()  (src/trusted_setup.rs:40-78)
-  std::unique_ptr<TrustedSetup> take(size_t n) const {
+  // g2_count: how many items also get their G2 point (the reference: all of them, src/trusted_setup.rs:64-72)
+  std::unique_ptr<TrustedSetup> take(size_t n, size_t g2_count = SIZE_MAX) const {
     kzg_setup* h = nullptr;
     ctx_->check(kzg_setup_generate(ctx_->get(), secret_.data(), 0, n, &h));
-    return std::make_unique<TrustedSetup>(ctx_, h);
+    auto out = std::make_unique<TrustedSetup>(ctx_, h);
+    ctx_->check(kzg_setup_generate_g2(ctx_->get(), h, secret_.data(), g2_count < n ? g2_count : n));
+    return out;
   }
  private:
   std::shared_ptr<Context> ctx_;
@@ -155,6 +217,42 @@ class Polynomial {
     return try_from(std::move(s));
   }
   static Polynomial from(const Scalar& c) { return Polynomial(c.is_zero() ? std::vector<Scalar>{} : std::vector<Scalar>{c}); }
+  // derived Deserialize keeps the coefficients as stored: no re-trimming (src/polynomial.rs:9-12)
+  static Polynomial from_raw_coefficients(std::vector<Scalar> v) { return Polynomial(std::move(v)); }
+  // Polynomial::sub (src/polynomial.rs:128-145)
+  Polynomial sub(const Polynomial& o) const {
+    std::vector<Scalar> co;
+    if (coefficients_.size() > o.coefficients_.size()) {
+      co = coefficients_;
+      for (size_t i = 0; i < o.coefficients_.size(); i++) co[i] = co[i].sub(o.coefficients_[i]);
+    } else {
+      for (auto& c : o.coefficients_) co.push_back(c.neg());
+      for (size_t i = 0; i < coefficients_.size(); i++) co[i] = coefficients_[i].add(co[i]);
+    }
+    return try_from(std::move(co));
+  }
+  // Polynomial::divide_by_root (src/polynomial.rs:150-195): one kzg_quotient call
+  Polynomial divide_by_root(const Context& ctx, const Scalar& root) const {
+    if (coefficients_.empty()) return Polynomial({});
+    if (coefficients_.size() == 1) {
+      if (coefficients_[0].is_zero()) return Polynomial({});
+      throw Error(KZG_E_CONSTANT_POLY, kzg_status_string(KZG_E_CONSTANT_POLY));
+    }
+    auto b = bytes(); std::vector<uint8_t> q(coefficients_.size() * 32); uint64_t ql = 0; std::array<uint8_t, 32> zero{};
+    ctx.check(kzg_quotient(ctx.get(), b.data(), coefficients_.size(), root.to_le_bytes().data(), zero.data(), q.data(), &ql));
+    std::vector<Scalar> co;
+    for (uint64_t i = 0; i < ql; i++) { std::array<uint8_t, 32> le; std::copy(q.begin() + 32 * i, q.begin() + 32 * i + 32, le.begin()); co.push_back(Scalar::from_le_bytes(le)); }
+    return try_from(std::move(co));
+  }
+  // impl Display (src/polynomial.rs:218-247)
+  std::string to_string() const {
+    if (coefficients_.empty()) return "0";
+    auto term = [](const Scalar& c, size_t d) { return c.to_string() + (d == 0 ? "" : d == 1 ? "x" : "x^" + std::to_string(d)); };
+    size_t n = coefficients_.size();
+    std::string out = term(coefficients_[n - 1], n - 1);
+    for (size_t i = n - 1; i-- > 0;) if (!coefficients_[i].is_zero()) out += " + " + term(coefficients_[i], i);
+    return out;
+  }
   uint32_t degree() const { return coefficients_.empty() ? 0 : (uint32_t)(coefficients_.size() - 1); }
   const std::vector<Scalar>& coefficients() const { return coefficients_; }
 
@@ -184,6 +282,16 @@ class Evaluation {
     setup.ctx()->check(kzg_open(setup.ctx()->get(), setup.handle(), b.data(), p.coefficients().size(), point.to_le_bytes().data(),
                                 result.to_le_bytes().data(), y, out));
     return curves::G1Point::raw(out);
+  }
+  // Evaluation::verify_proof (src/polynomial.rs:276-294); setup[1] must exist (the reference indexes it unguarded)
+  bool verify_proof(const curves::G1Point& proof, const curves::G1Point& commitment, const trusted_setup::TrustedSetup& setup) const {
+    trusted_setup::SetupArtifact a1 = setup.at(1);
+    if (!a1.has_g2) throw Error(KZG_E_SETUP_TOO_SHORT, "setup item 1 carries no G2 point");
+    int32_t ok = 0;
+    int32_t st = kzg_verify_proof(proof.compressed().data(), commitment.compressed().data(), point.to_le_bytes().data(),
+                                  result.to_le_bytes().data(), a1.g2.compressed().data(), &ok);
+    if (st != KZG_OK) throw Error(st, kzg_status_string(st));
+    return ok != 0;
   }
 };
 

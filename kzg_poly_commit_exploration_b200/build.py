@@ -49,12 +49,30 @@ def build(force: bool = False) -> str:
         objs = list(ex.map(_compile, SOURCES))
     if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-o", OUT, *objs]
+               "-Xlinker", "-soname=libkzg_b200.so", "-o", OUT, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return OUT
 
 
+CLI_SRC = os.path.join(HERE, "..", "cli", "kzg_cli.cpp")
+CLI_OUT = os.path.join(HERE, "..", "cli", "kzg-cli")
+
+
+def build_cli() -> str:
+    """The reference's command-line tool (src/main.rs) over the C ABI: plain g++, links libkzg_b200.so."""
+    deps = [CLI_SRC, OUT, os.path.join(HERE, "..", "include", "kzg_b200.hpp"), os.path.join(HERE, "..", "include", "kzg_b200.h")]
+    if os.path.exists(CLI_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(CLI_OUT) for d in deps):
+        return CLI_OUT
+    cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(HERE, "..", "include"), CLI_SRC, "-o", CLI_OUT,
+           "-L", HERE, "-l:libkzg_b200.so", "-Wl,-rpath,$ORIGIN/../kzg_poly_commit_exploration_b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for the CLI:\n{r.stdout}\n{r.stderr}")
+    return CLI_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_cli())
