@@ -18,6 +18,10 @@ extern "C" {
     pub fn kzg_setup_import_g1(ctx: *mut kzg_ctx, g1_c48: *const u8, n: u64, out: *mut *mut kzg_setup) -> i32;
     pub fn kzg_setup_export_g1(ctx: *mut kzg_ctx, s: *const kzg_setup, first: u64, count: u64, out_c48: *mut u8) -> i32;
     pub fn kzg_setup_len(s: *const kzg_setup) -> u64;
+    pub fn kzg_setup_generate_g2(ctx: *mut kzg_ctx, s: *mut kzg_setup, secret_be: *const u8, count: u64) -> i32;
+    pub fn kzg_setup_import_g2(ctx: *mut kzg_ctx, s: *mut kzg_setup, g2_c96: *const u8, count: u64) -> i32;
+    pub fn kzg_setup_export_g2(ctx: *mut kzg_ctx, s: *const kzg_setup, first: u64, count: u64, out_c96: *mut u8) -> i32;
+    pub fn kzg_setup_g2_len(s: *const kzg_setup) -> u64;
     pub fn kzg_setup_destroy(s: *mut kzg_setup);
     pub fn kzg_commit(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, n: u64, out_c48: *mut u8) -> i32;
     pub fn kzg_evaluate(ctx: *mut kzg_ctx, coeffs_le32: *const u8, n: u64, z_le: *const u8, y_le: *mut u8) -> i32;
@@ -26,4 +30,10 @@ extern "C" {
     pub fn kzg_commit_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64, out_c48: *mut u8) -> i32;
     pub fn kzg_open_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64,
                           z_le32: *const u8, y_le32: *mut u8, proofs_c48: *mut u8) -> i32;
+    // host-side G2 / pairing (only needed when blst is dropped altogether)
+    pub fn kzg_g2_from_scalar(k_le: *const u8, out: *mut u8);
+    pub fn kzg_g2_sub(a: *const u8, b: *const u8, out: *mut u8) -> i32;
+    pub fn kzg_pairing_equal(a1: *const u8, b1: *const u8, a2: *const u8, b2: *const u8, equal: *mut i32) -> i32;
+    pub fn kzg_verify_proof(proof: *const u8, commitment: *const u8, z_le: *const u8, y_le: *const u8,
+                            g2_tau: *const u8, ok: *mut i32) -> i32;
 }
