@@ -90,6 +90,8 @@ int32_t msm_fixed_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars
                         uint64_t n, uint64_t stride_scalars, G1Xyzz* out_dev) {
   if (blobs == 0) return KZG_OK;
   if (!s->fix_tab || n > s->fix_n) return fail(ctx, KZG_E_BAD_ARG, "fixed-base table not prepared for this size");
+  if (n > 0 && s->fix_w <= 32 && blobs >= (uint64_t)ctx->opt_tree_min_rows)
+    return msm_fixed_batch_tree(ctx, s, scalars_dev, blobs, n, stride_scalars, out_dev);
   if (blobs > 65535) return fail(ctx, KZG_E_BAD_ARG, "more than 65535 blobs per call");
   // enough blocks to fill the machine: small batches split each MSM across blocks
   uint32_t splits = 1;

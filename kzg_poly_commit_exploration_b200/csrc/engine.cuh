@@ -16,6 +16,7 @@ enum ScratchSlot {
   SCR_BUCKET_START, SCR_BUCKETS, SCR_RED_A, SCR_RED_B, SCR_HEAVY,
   SCR_XYZZ_TMP, SCR_PREFIX, SCR_QUOT, SCR_SEG, SCR_OUT, SCR_MISC, SCR_FR_A, SCR_FR_B,
   SCR_BATCH_PTS, SCR_BATCH_AFF, SCR_PARTIALS, SCR_HEAVY_PARTS,
+  SCR_TREE_A, SCR_TREE_B, SCR_TREE_PREFIX, SCR_TREE_TOT,
   SCR_COUNT
 };
 
@@ -40,6 +41,9 @@ struct kzg_ctx {
   int opt_reduce_chunk = 16;
   int opt_heavy_cap = 1024;
   int opt_acc_split = -1;              // log2(threads per bucket), -1 = auto
+  int opt_tree_min_rows = 512;         // batches of at least this many rows take the affine tree path (batch_tree.cu)
+  int opt_tree_chunk_rows = 2048;      // rows reduced together (bounds the scratch: ~8 KiB * n/4096 * W/2 per row... see DESIGN)
+  int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
 };
@@ -133,6 +137,11 @@ int32_t finalize_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, uint
 // blobs MSMs of n scalars each against the fixed-base table; out: blobs XYZZ
 int32_t msm_fixed_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t blobs,
                         uint64_t n, uint64_t stride_scalars, G1Xyzz* out_dev);
+
+// ---- batch_tree.cu (K5') ---------------------------------------------------------------------
+// same contract as msm_fixed_batch; affine pairwise tree with grid-wide shared inversions (large batches)
+int32_t msm_fixed_batch_tree(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t rows,
+                             uint64_t n, uint64_t stride_scalars, G1Xyzz* out_dev);
 
 // ---- probe.cu --------------------------------------------------------------------------------
 int32_t probe_imad(kzg_ctx* ctx, double* wide_mac_per_s);

@@ -282,58 +282,136 @@ KZG_HD void pow_limbs(F& o, const F& a, const uint32_t* e) {
 KZG_HD void inv(Fq& o, const Fq& a) { pow_limbs<Fq, 12>(o, a, KZG_C(FQ_PM2)); }
 KZG_HD void inv(Fr& o, const Fr& a) { pow_limbs<Fr, 8>(o, a, KZG_C(FR_PM2)); }
 
-// Inversion by the binary extended Euclid algorithm (shifts and subtractions only): ~25x fewer
-// instructions than Fermat's a^(q-2) for a single element, at the price of data-dependent control flow —
-// used where ONE thread inverts ONE value (the final to-affine of a commitment).  Montgomery in/out.
-KZG_HD void inv_gcd(Fq& o, const Fq& a) {
-  if (is_zero(a)) { set_zero(o); return; }
-  uint32_t u[12], v[12], x1[12], x2[12];
+// Inversion by the optimised binary GCD of Pornin ("Optimized Binary GCD for Modular Inversion", 2020):
+// the 381-bit operands a, b are replaced, 30 steps at a time, by 62-bit approximations (their top 32 bits
+// and their exact low 30 bits); the 30 plain binary-GCD steps run on those two words and yield a 2x2
+// integer matrix (|f|+|g| <= 2^30) that is then applied once to (a, b) — exact division by 2^30 — and to
+// the Bezout pair (u, v) — division by 2^30 modulo q, Montgomery style.  28 outer iterations cover the
+// 2*381 - 1 steps a 381-bit modulus can need; control flow is identical for every input, so a warp of
+// independent inversions never diverges.  ~12x fewer instructions than Fermat's a^(q-2): used for the
+// final to-affine of a commitment, the top of the grid-wide batch inversions (batch_tree.cu), Fq2
+// inversion.  Montgomery in, Montgomery out; inv_gcd(0) = 0.
+namespace bingcd {
+// t = +-fa * a +- ga * b as a 13-limb two's-complement integer (fa, ga < 2^31 magnitudes, signs sf, sg)
+KZG_HD void lin13(uint32_t* t, uint32_t fa, bool sf, const uint32_t* a, uint32_t ga, bool sg, const uint32_t* b) {
+  uint32_t pa[13], pb[13];
+  uint64_t c = 0;
 #pragma unroll
-  for (int i = 0; i < 12; i++) { u[i] = a.v[i]; v[i] = KZG_C(FQ_P)[i]; x1[i] = 0; x2[i] = 0; }
-  x1[0] = 1;
-  auto is_one = [](const uint32_t* w) {
-    uint32_t acc = w[0] ^ 1u;
-    for (int i = 1; i < 12; i++) acc |= w[i];
-    return acc == 0;
-  };
-  auto shr1 = [](uint32_t* w) {
-    for (int i = 0; i < 11; i++) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
-    w[11] >>= 1;
-  };
-  auto half_mod = [&](uint32_t* x) {          // x <- x/2 mod p ; x + p < 2^382 fits 12 limbs
-    if (x[0] & 1u) {
-      uint64_t c = 0;
-      for (int i = 0; i < 12; i++) { c += (uint64_t)x[i] + KZG_C(FQ_P)[i]; x[i] = (uint32_t)c; c >>= 32; }
-    }
-    shr1(x);
-  };
-  auto ge = [](const uint32_t* x, const uint32_t* y) {
-    for (int i = 11; i >= 0; i--) { if (x[i] != y[i]) return x[i] > y[i]; }
-    return true;
-  };
-  auto sub_in = [](uint32_t* x, const uint32_t* y) {   // x -= y, x >= y
-    uint64_t br = 0;
-    for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)x[i] - y[i] - br; x[i] = (uint32_t)d; br = (d >> 63) & 1; }
-  };
-  auto sub_modp = [&](uint32_t* x, const uint32_t* y) {  // x <- x - y mod p
-    uint64_t br = 0;
-    for (int i = 0; i < 12; i++) { uint64_t d = (uint64_t)x[i] - y[i] - br; x[i] = (uint32_t)d; br = (d >> 63) & 1; }
-    if (br) {
-      uint64_t c = 0;
-      for (int i = 0; i < 12; i++) { c += (uint64_t)x[i] + KZG_C(FQ_P)[i]; x[i] = (uint32_t)c; c >>= 32; }
-    }
-  };
-  while (!is_one(u) && !is_one(v)) {
-    while (!(u[0] & 1u)) { shr1(u); half_mod(x1); }
-    while (!(v[0] & 1u)) { shr1(v); half_mod(x2); }
-    if (ge(u, v)) { sub_in(u, v); sub_modp(x1, x2); }
-    else { sub_in(v, u); sub_modp(x2, x1); }
+  for (int i = 0; i < 12; i++) { c += (uint64_t)fa * a[i]; pa[i] = (uint32_t)c; c >>= 32; }
+  pa[12] = (uint32_t)c;
+  c = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) { c += (uint64_t)ga * b[i]; pb[i] = (uint32_t)c; c >>= 32; }
+  pb[12] = (uint32_t)c;
+  const uint32_t ma = sf ? 0xFFFFFFFFu : 0u, mb = sg ? 0xFFFFFFFFu : 0u;
+  uint64_t ca = sf ? 1u : 0u, cb = sg ? 1u : 0u, cs = 0;
+#pragma unroll
+  for (int i = 0; i < 13; i++) {
+    ca += (uint64_t)(pa[i] ^ ma); uint32_t xa = (uint32_t)ca; ca >>= 32;      // conditional negation
+    cb += (uint64_t)(pb[i] ^ mb); uint32_t xb = (uint32_t)cb; cb >>= 32;
+    cs += (uint64_t)xa + xb; t[i] = (uint32_t)cs; cs >>= 32;
   }
-  Fq z, r2;
-  const uint32_t* res = is_one(u) ? x1 : x2;
+}
+KZG_HD void neg13(uint32_t* t) {
+  uint64_t c = 1;
 #pragma unroll
-  for (int i = 0; i < 12; i++) { z.v[i] = res[i]; r2.v[i] = KZG_C(FQ_R2)[i]; }
-  mul(z, z, r2);   // (aR)^-1 * R^2 * R^-1 = a^-1
+  for (int i = 0; i < 13; i++) { c += (uint64_t)(~t[i]); t[i] = (uint32_t)c; c >>= 32; }
+}
+// bits [sh, sh+32) of a 384-bit integer, sh in [30, 352], without dynamic register indexing
+KZG_HD uint32_t extract32(const uint32_t* a, uint32_t sh) {
+  const uint32_t w = sh >> 5, off = sh & 31;
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    lo = (i == (int)w) ? a[i] : lo;
+    hi = (i == (int)w + 1) ? a[i] : hi;
+  }
+  return off ? ((lo >> off) | (hi << (32 - off))) : lo;
+}
+// dst = t / 2^30 mod q for a 13-limb two's-complement t in (-2^30 q, 2^30 q): add the multiple of q that
+// clears the low 30 bits (Montgomery step), shift, fold the result from (-q, 2q) into [0, q)
+KZG_HD void div30_mod_q(uint32_t* dst, uint32_t* t) {
+  const uint32_t m = (t[0] * FQ_NEGINV30) & 0x3FFFFFFFu;
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) { c += (uint64_t)m * KZG_C(FQ_P)[i] + t[i]; t[i] = (uint32_t)c; c >>= 32; }
+  t[12] = (uint32_t)(c + t[12]);
+  const bool negative = (t[12] >> 31) != 0;
+  uint32_t r[12], w[12], s2[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) r[i] = (t[i] >> 30) | (t[i + 1] << 2);
+  uint64_t cc = 0; uint32_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    cc += (uint64_t)r[i] + KZG_C(FQ_P)[i]; w[i] = (uint32_t)cc; cc >>= 32;
+    uint64_t d = (uint64_t)r[i] - KZG_C(FQ_P)[i] - br; s2[i] = (uint32_t)d; br = (uint32_t)(d >> 63);
+  }
+  const bool ge = !negative && br == 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) dst[i] = negative ? w[i] : (ge ? s2[i] : r[i]);
+}
+}  // namespace bingcd
+
+KZG_HD void inv_gcd(Fq& o, const Fq& x) {
+  uint32_t a[12], b[12], u[12], v[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { a[i] = x.v[i]; b[i] = KZG_C(FQ_P)[i]; u[i] = 0; v[i] = 0; }
+  u[0] = 1;
+#pragma unroll 1
+  for (int it = 0; it < 28; it++) {
+    // ---- 62-bit approximations: n = max(len(a), len(b), 62); top 32 bits above bit n-32, low 30 bits exact
+    uint32_t top = 0, topw = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      uint32_t c = a[i] | b[i];
+      if (c) { top = c; topw = (uint32_t)i; }
+    }
+    uint32_t blen = 0;
+    for (uint32_t t = top; t; t >>= 1) blen++;               // <= 32 steps; host + device
+    uint32_t n = topw * 32 + blen;
+    if (n < 62) n = 62;
+    const uint32_t sh = n - 32;
+    uint64_t xa = ((uint64_t)bingcd::extract32(a, sh) << 30) | (a[0] & 0x3FFFFFFFu);
+    uint64_t xb = ((uint64_t)bingcd::extract32(b, sh) << 30) | (b[0] & 0x3FFFFFFFu);
+    // ---- 30 binary-GCD steps on the approximations
+    int32_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+#pragma unroll 1
+    for (int i = 0; i < 30; i++) {
+      const bool odd = (xa & 1u) != 0;
+      const bool swp = odd && (xa < xb);
+      if (swp) {
+        uint64_t tx = xa; xa = xb; xb = tx;
+        int32_t tf = f0; f0 = f1; f1 = tf;
+        int32_t tg = g0; g0 = g1; g1 = tg;
+      }
+      if (odd) { xa -= xb; f0 -= f1; g0 -= g1; }
+      xa >>= 1;
+      f1 <<= 1; g1 <<= 1;
+    }
+    // ---- (a, b) <- (f0 a + g0 b, f1 a + g1 b) / 2^30, made non-negative
+    uint32_t ta[13], tb[13];
+    bingcd::lin13(ta, (uint32_t)(f0 < 0 ? -f0 : f0), f0 < 0, a, (uint32_t)(g0 < 0 ? -g0 : g0), g0 < 0, b);
+    bingcd::lin13(tb, (uint32_t)(f1 < 0 ? -f1 : f1), f1 < 0, a, (uint32_t)(g1 < 0 ? -g1 : g1), g1 < 0, b);
+    if (ta[12] >> 31) { bingcd::neg13(ta); f0 = -f0; g0 = -g0; }
+    if (tb[12] >> 31) { bingcd::neg13(tb); f1 = -f1; g1 = -g1; }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      a[i] = (ta[i] >> 30) | (ta[i + 1] << 2);
+      b[i] = (tb[i] >> 30) | (tb[i + 1] << 2);
+    }
+    // ---- (u, v) <- the same combination / 2^30 mod q
+    uint32_t tu[13], tv[13];
+    bingcd::lin13(tu, (uint32_t)(f0 < 0 ? -f0 : f0), f0 < 0, u, (uint32_t)(g0 < 0 ? -g0 : g0), g0 < 0, v);
+    bingcd::lin13(tv, (uint32_t)(f1 < 0 ? -f1 : f1), f1 < 0, u, (uint32_t)(g1 < 0 ? -g1 : g1), g1 < 0, v);
+    bingcd::div30_mod_q(u, tu);
+    bingcd::div30_mod_q(v, tv);
+  }
+  // gcd reached: b = 1, v = x^-1 (as integers mod q); x = a_mont = aR  ->  v = a^-1 R^-1
+  Fq z, r2;
+#pragma unroll
+  for (int i = 0; i < 12; i++) { z.v[i] = v[i]; r2.v[i] = KZG_C(FQ_R2)[i]; }
+  if (is_zero(x)) { set_zero(o); return; }
+  mul(z, z, r2);   // a^-1
   mul(o, z, r2);   // a^-1 * R
 }
 

@@ -333,6 +333,63 @@ def test_blob_batch_small(ctx, c):
     st.close()
 
 
+# ---- affine-tree batch path (batch_tree.cu): forced on small batches, every round, chunked --------------------
+@pytest.mark.parametrize("c,n,blobs,chunk", [(8, 100, 7, 3), (9, 33, 5, 2048), (13, 64, 4, 2)])
+def test_blob_batch_tree_path(ctx, c, n, blobs, chunk):
+    st = ctx.setup_generate(SECRET, n)
+    st.prepare_fixed(n, c)
+    coeffs = bytearray(util.scalar_stream_bytes(0xC4 + c, blobs * n))
+    # adversarial rows: all-zero, all-equal, r-1, alternating v / -v (cancellations inside and across coefficients)
+    v = O.scalar_stream(77, 0)
+    special = {0: [0] * n, 1: [v] * n, 2: [O.R - 1] * n, 3: [v if i % 2 == 0 else O.R - v for i in range(n)]}
+    for b, ints in special.items():
+        if b < blobs:
+            coeffs[b * n * 32: (b + 1) * n * 32] = util.from_ints(ints)
+    coeffs = bytes(coeffs)
+    zs = util.scalar_stream_bytes(0xC4F, blobs)
+    for name, val in (("tree_min_rows", 1), ("tree_min_pairs", 1), ("tree_chunk_rows", chunk)):
+        ctx.set_option(name, val)
+    try:
+        commits = ctx.commit_batch(st, coeffs, blobs, n)
+        ys, proofs = ctx.open_batch(st, coeffs, blobs, n, zs)
+        ctx.set_option("tree_min_pairs", 1 << 19)          # round 1 only, then the XYZZ fold
+        commits2 = ctx.commit_batch(st, coeffs, blobs, n)
+    finally:
+        for name, val in (("tree_min_rows", 512), ("tree_min_pairs", 1 << 19), ("tree_chunk_rows", 2048)):
+            ctx.set_option(name, val)
+    assert commits2 == commits
+    for b in range(blobs):
+        co = util.to_ints(coeffs[b * n * 32: (b + 1) * n * 32])
+        z = int.from_bytes(zs[32 * b: 32 * b + 32], "little")
+        assert commits[48 * b: 48 * b + 48] == O.g1_compress(O.commit_known_secret(co, S)), b
+        assert int.from_bytes(ys[32 * b: 32 * b + 32], "little") == O.horner(co, z), b
+        assert proofs[48 * b: 48 * b + 48] == O.g1_compress(O.proof_known_secret(co, S, z)), b
+    st.close()
+
+
+@pytest.mark.parametrize("secret_int", [0, 1, O.R - 1])
+def test_blob_batch_tree_path_degenerate_setups(ctx, secret_int):
+    """s = 1: every base is G (all pairs double or cancel); s = 0: bases beyond the first are infinity."""
+    n, blobs, c = 40, 4, 8
+    sec = secret_int.to_bytes(32, "big")
+    st = ctx.setup_generate(sec, n)
+    st.prepare_fixed(n, c)
+    coeffs = bytearray(util.scalar_stream_bytes(3, blobs * n))
+    coeffs[: n * 32] = util.from_ints([5] * n)
+    coeffs[n * 32: 2 * n * 32] = util.from_ints([7 if i % 2 == 0 else O.R - 7 for i in range(n)])
+    coeffs = bytes(coeffs)
+    for name, val in (("tree_min_rows", 1), ("tree_min_pairs", 1)):
+        ctx.set_option(name, val)
+    try:
+        commits = ctx.commit_batch(st, coeffs, blobs, n)
+    finally:
+        ctx.set_option("tree_min_rows", 512); ctx.set_option("tree_min_pairs", 1 << 19)
+    for b in range(blobs):
+        co = util.to_ints(coeffs[b * n * 32: (b + 1) * n * 32])
+        assert commits[48 * b: 48 * b + 48] == O.g1_compress(O.commit_known_secret(co, secret_int)), b
+    st.close()
+
+
 def test_blob_batch_without_fixed_table_uses_bucket_msm(ctx, setup8k):
     n, blobs = 300, 3
     coeffs = util.scalar_stream_bytes(21, blobs * n)
