@@ -16,7 +16,7 @@ enum ScratchSlot {
   SCR_BUCKET_START, SCR_BUCKETS, SCR_RED_A, SCR_RED_B, SCR_HEAVY,
   SCR_XYZZ_TMP, SCR_PREFIX, SCR_QUOT, SCR_SEG, SCR_OUT, SCR_MISC, SCR_FR_A, SCR_FR_B,
   SCR_BATCH_PTS, SCR_BATCH_AFF, SCR_PARTIALS, SCR_HEAVY_PARTS,
-  SCR_TREE_A, SCR_TREE_B, SCR_TREE_PREFIX, SCR_TREE_TOT,
+  SCR_TREE_A, SCR_TREE_B, SCR_TREE_PREFIX, SCR_TREE_TOT, SCR_TREE_SEG, SCR_TREE_IOTA,
   SCR_COUNT
 };
 
@@ -44,6 +44,7 @@ struct kzg_ctx {
   int opt_tree_min_rows = 512;         // batches of at least this many rows take the affine tree path (batch_tree.cu)
   int opt_tree_chunk_rows = 2048;      // rows reduced together (bounds the scratch: ~8 KiB * n/4096 * W/2 per row... see DESIGN)
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
+  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 from 2^23 entries)
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
 };
@@ -142,6 +143,17 @@ int32_t msm_fixed_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars
 // same contract as msm_fixed_batch; affine pairwise tree with grid-wide shared inversions (large batches)
 int32_t msm_fixed_batch_tree(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t rows,
                              uint64_t n, uint64_t stride_scalars, G1Xyzz* out_dev);
+
+// grid-wide batch inversion: v[i] <- 1 / v[i], i < N, no zeros; ws holds invert_scratch_elems(N, top) Fq
+size_t invert_scratch_elems(uint64_t N, uint64_t top);
+int32_t batch_invert_inplace(kzg_ctx* ctx, Fq* v, uint64_t N, Fq* ws, uint64_t top);
+
+// ---- msm_tree.cu (K2') ----------------------------------------------------------------------
+// `rounds` halvings of every bucket's sorted entries in affine coordinates (shared inversions).  In: bucket
+// bounds start[0..M] over vals (table index | sign << 31).  Out: dense affine points + their bounds.
+int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const G1Affine* tab,
+                        uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
+                        const uint32_t** seg_out, const uint32_t** iota_out, uint64_t* entries_out);
 
 // ---- probe.cu --------------------------------------------------------------------------------
 int32_t probe_imad(kzg_ctx* ctx, double* wide_mac_per_s);

@@ -222,21 +222,31 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   KZG_LAUNCHED(ctx);
   KZG_CUDA_OK(ctx, cudaMemsetAsync(heavy_count, 0, 4, ctx->stream));
 
+  // optional affine halving rounds (msm_tree.cu): the accumulate kernel then walks dense affine points
+  const uint32_t* acc_start = reinterpret_cast<uint32_t*>(st);
+  const uint32_t* acc_vals = reinterpret_cast<uint32_t*>(vb);
+  const G1Affine* acc_tab = s->msm_tab;
+  uint64_t acc_entries = total;
+  int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : (total >= (1ull << 23) ? 3 : 0);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (rounds > 0)
+    KZG_TRY(msm_tree_rounds(ctx, acc_start, acc_vals, acc_tab, half, total, rounds, &acc_tab, &acc_start, &acc_vals,
+                            &acc_entries));
+
   // threads per bucket: aim for ~2^18 accumulate threads
   uint32_t logT = 0;
   if (ctx->opt_acc_split >= 0) logT = (uint32_t)ctx->opt_acc_split;
-  else while ((half << logT) < (1u << 18) && (total >> (c - 1 + logT)) > 32) logT++;
+  else while ((half << logT) < (1u << 18) && (acc_entries >> (c - 1 + logT)) > (rounds > 0 ? 4 : 32)) logT++;
   const uint32_t T = 1u << logT;
   void* parts = bk;
   if (logT) KZG_TRY(scratch_get(ctx, SCR_PARTIALS, ((size_t)half << logT) * sizeof(G1Xyzz), &parts));
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   {
     auto kern = k_bucket_acc<3>;
     if (ctx->opt_acc_minblocks == 4) kern = k_bucket_acc<4>;
     else if (ctx->opt_acc_minblocks == 5) kern = k_bucket_acc<5>;
     else if (ctx->opt_acc_minblocks == 6) kern = k_bucket_acc<6>;
     kern<<<blocks_for((uint64_t)half << logT, 128), 128, 0, ctx->stream>>>(
-        reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb), s->msm_tab, half, logT, heavy_cap,
+        acc_start, acc_vals, acc_tab, half, logT, heavy_cap,
         reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
   }
   KZG_LAUNCHED(ctx);
@@ -245,8 +255,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
     void* hp;
     KZG_TRY(scratch_get(ctx, SCR_HEAVY_PARTS, heavy_max * HEAVY_BLOCKS * sizeof(G1Xyzz), &hp));
     k_bucket_heavy<<<dim3(HEAVY_BLOCKS, 16), 128, 0, ctx->stream>>>(
-        reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb), s->msm_tab, reinterpret_cast<G1Xyzz*>(hp),
-        heavy_list, heavy_count);
+        acc_start, acc_vals, acc_tab, reinterpret_cast<G1Xyzz*>(hp), heavy_list, heavy_count);
     KZG_LAUNCHED(ctx);
     k_heavy_fold<<<8, 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(hp), logT, reinterpret_cast<G1Xyzz*>(parts),
                                              heavy_list, heavy_count);

@@ -1,0 +1,194 @@
+// K2' — the first rounds of the bucket accumulation in affine coordinates.
+//
+// After the radix sort every bucket owns a contiguous run of (table index, sign) entries; all buckets together
+// hold W*n of them (16.8 M at n = 2^20).  k_bucket_acc adds them one by one into XYZZ registers: 10 Fq products
+// per addition.  Here the runs are first HALVED a few times: neighbouring entries of a run are added pairwise in
+// affine coordinates, all pairs of all buckets in one grid, with one shared inversion per round (Montgomery's
+// trick across the grid, batch_tree.cu) — 6.6 products per addition.  Three rounds do 7/8 of all additions;
+// what is left (W*n/8 dense affine points, same bucket structure) goes to k_bucket_acc and the usual tail.
+// Only worth it when a round has millions of independent additions (its inversion chain is ~0.15 ms of
+// latency): msm_bucket enables it from 2^23 entries.  Pairs never cross a bucket; a run of odd length passes
+// its last entry through; additions are complete (infinity, P = Q, P = -Q).
+#include "affine_tree.cuh"
+
+namespace kzg {
+
+constexpr int ST_K = 8;          // consecutive output points per thread
+
+// seg_out[b] = sum_{b' < b} ceil(len(b') / 2), b = 0 .. M  (one block)
+__global__ void __launch_bounds__(1024)
+k_seg_scan(const uint32_t* __restrict__ seg_in, uint32_t M, uint32_t* __restrict__ seg_out) {
+  __shared__ uint32_t sh[1024];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t per = (M + 1023) / 1024;
+  const uint32_t lo = tid * per < M ? tid * per : M;
+  const uint32_t hi = lo + per < M ? lo + per : M;
+  uint32_t sum = 0;
+  for (uint32_t b = lo; b < hi; b++) sum += (seg_in[b + 1] - seg_in[b] + 1) >> 1;
+  sh[tid] = sum;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = tid >= d ? sh[tid - d] : 0;
+    __syncthreads();
+    sh[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = tid ? sh[tid - 1] : 0;
+  for (uint32_t b = lo; b < hi; b++) { seg_out[b] = run; run += (seg_in[b + 1] - seg_in[b] + 1) >> 1; }
+  if (tid == 1023) seg_out[M] = sh[1023];
+}
+
+__global__ void k_iota(uint32_t* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+
+// bucket of output position p: the largest b < M with seg_out[b] <= p (empty buckets share their bound with the
+// next non-empty one, and "largest" picks that one)
+__device__ __forceinline__ uint32_t bucket_of(const uint32_t* __restrict__ seg_out, uint32_t M, uint32_t p) {
+  uint32_t lo = 0, hi = M - 1;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    if (__ldg(seg_out + mid) <= p) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+struct PairRef { const G1Affine* p1; const G1Affine* p2; bool n1, n2; };
+
+template <bool R1>
+__device__ __forceinline__ PairRef pair_ref(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out,
+                                            const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src,
+                                            uint32_t b, uint32_t p) {
+  const uint32_t q = p - __ldg(seg_out + b);
+  const uint32_t s = __ldg(seg_in + b), len = __ldg(seg_in + b + 1) - s;
+  const uint32_t e1 = s + 2 * q;
+  const bool has2 = 2 * q + 1 < len;
+  PairRef r;
+  if (R1) {
+    const uint32_t v1 = __ldg(vals + e1), v2 = has2 ? __ldg(vals + e1 + 1) : 0u;
+    r.p1 = src + (v1 & 0x7FFFFFFFu); r.n1 = (v1 >> 31) != 0;
+    r.p2 = has2 ? src + (v2 & 0x7FFFFFFFu) : nullptr; r.n2 = (v2 >> 31) != 0;
+  } else {
+    r.p1 = src + e1; r.n1 = false;
+    r.p2 = has2 ? src + e1 + 1 : nullptr; r.n2 = false;
+  }
+  return r;
+}
+
+template <bool R1>
+__global__ void __launch_bounds__(128)
+k_seg_den(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
+          const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T,
+          Fq* __restrict__ prefix, Fq* __restrict__ tot) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t NP = __ldg(seg_out + M);
+  Fq acc; set_one(acc);
+  const uint64_t p0 = t * ST_K;
+  if (p0 < NP) {
+    uint32_t b = bucket_of(seg_out, M, (uint32_t)p0);
+#pragma unroll 1
+    for (int k = 0; k < ST_K; k++) {
+      const uint32_t p = (uint32_t)p0 + k;
+      if (p >= NP) break;
+      while (__ldg(seg_out + b + 1) <= p) b++;
+      PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p);
+      Fq d;
+      pair_den(d, r.p1, r.n1, r.p2, r.n2);
+      st_fq(prefix + (size_t)k * T + t, acc);
+      mul(acc, acc, d);
+    }
+  }
+  st_fq(tot + t, acc);
+}
+
+template <bool R1>
+__global__ void __launch_bounds__(128)
+k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
+          const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T,
+          const Fq* __restrict__ prefix, const Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t NP = __ldg(seg_out + M);
+  const uint64_t p0 = t * ST_K;
+  if (p0 >= NP) return;
+  uint32_t bk[ST_K];
+  int kmax = 0;
+  {
+    uint32_t b = bucket_of(seg_out, M, (uint32_t)p0);
+    for (int k = 0; k < ST_K; k++) {
+      const uint32_t p = (uint32_t)p0 + k;
+      if (p >= NP) break;
+      while (__ldg(seg_out + b + 1) <= p) b++;
+      bk[k] = b; kmax = k + 1;
+    }
+  }
+  Fq inv; ld_fq_plain(inv, tot_inv + t);
+#pragma unroll 1
+  for (int k = kmax - 1; k >= 0; k--) {
+    const uint32_t p = (uint32_t)p0 + k;
+    PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, bk[k], p);
+    Fq d, pf, dinv;
+    pair_den(d, r.p1, r.n1, r.p2, r.n2);
+    ld_fq_plain(pf, prefix + (size_t)k * T + t);
+    mul(dinv, inv, pf);
+    mul(inv, inv, d);
+    G1Affine a, b2, o;
+    ld_point(a, r.p1, r.n1);
+    ld_point(b2, r.p2, r.n2);
+    pair_add(o, a, b2, dinv);
+    st_fq(&out[p].x, o.x); st_fq(&out[p].y, o.y);
+  }
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const G1Affine* tab,
+                        uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
+                        const uint32_t** seg_out_p, const uint32_t** iota_out, uint64_t* entries_out) {
+  const uint64_t top = 8192;
+  // upper bounds on the number of points after each round (exact counts stay on the device)
+  auto halve = [M](uint64_t e) { uint64_t h = (e + M) / 2 + 1; return h < e ? h : e; };   // never grows
+  const uint64_t e1 = halve(entries);
+  const uint64_t e2 = halve(e1);
+  const uint64_t T1 = (e1 + ST_K - 1) / ST_K;
+  void *A, *B, *PF, *TW, *SG, *IO;
+  KZG_TRY(scratch_get(ctx, SCR_TREE_A, e1 * sizeof(G1Affine), &A));
+  KZG_TRY(scratch_get(ctx, SCR_TREE_B, e2 * sizeof(G1Affine), &B));
+  KZG_TRY(scratch_get(ctx, SCR_TREE_PREFIX, (T1 * ST_K + 16) * sizeof(Fq), &PF));
+  KZG_TRY(scratch_get(ctx, SCR_TREE_TOT, (T1 + invert_scratch_elems(T1, top)) * sizeof(Fq), &TW));
+  KZG_TRY(scratch_get(ctx, SCR_TREE_SEG, 2 * ((size_t)M + 2) * 4, &SG));
+  Fq* prefix = reinterpret_cast<Fq*>(PF);
+  Fq* tot = reinterpret_cast<Fq*>(TW);
+  Fq* inv_ws = tot + T1;
+  uint32_t* seg[2] = {reinterpret_cast<uint32_t*>(SG), reinterpret_cast<uint32_t*>(SG) + M + 2};
+  G1Affine* buf[2] = {reinterpret_cast<G1Affine*>(A), reinterpret_cast<G1Affine*>(B)};
+
+  const uint32_t* seg_in = start_dev;
+  const G1Affine* src = tab;
+  uint64_t bound = entries;
+  for (int r = 0; r < rounds; r++) {
+    bound = halve(bound);
+    const uint64_t T = (bound + ST_K - 1) / ST_K;
+    uint32_t* so = seg[r & 1];
+    G1Affine* out = buf[r & 1];
+    k_seg_scan<<<1, 1024, 0, ctx->stream>>>(seg_in, M, so);
+    KZG_LAUNCHED(ctx);
+    if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, prefix, tot);
+    else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot);
+    KZG_LAUNCHED(ctx);
+    KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
+    if (r == 0) k_seg_add<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, prefix, tot, out);
+    else k_seg_add<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot, out);
+    KZG_LAUNCHED(ctx);
+    seg_in = so; src = out;
+  }
+  KZG_TRY(scratch_get(ctx, SCR_TREE_IOTA, (bound + 16) * 4, &IO));
+  k_iota<<<blocks_for(bound, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(IO), bound);
+  KZG_LAUNCHED(ctx);
+  *pts_out = src; *seg_out_p = seg_in; *iota_out = reinterpret_cast<uint32_t*>(IO); *entries_out = bound;
+  return KZG_OK;
+}
+
+}  // namespace kzg

@@ -287,6 +287,13 @@ def test_commit_adversarial_scalars(ctx, setup8k, kind):
         ints = [v if i % 2 == 0 else O.R - v for i in range(n)]
     got = ctx.msm_g1(setup8k, util.from_ints(ints))
     assert got == O.g1_compress(O.commit_known_secret(ints, S))
+    # the same through the affine halving rounds of msm_tree.cu (doublings, cancellations, odd runs, empty buckets)
+    for rounds in (1, 4):
+        ctx.set_option("msm_tree_rounds", rounds)
+        try:
+            assert ctx.msm_g1(setup8k, util.from_ints(ints)) == got, rounds
+        finally:
+            ctx.set_option("msm_tree_rounds", -1)
 
 
 @pytest.mark.parametrize("c", [4, 7, 11, 13, 16, 17, 19])
@@ -301,6 +308,13 @@ def test_msm_window_sizes(ctx, c):
         assert ctx.msm_g1(st, scal) == O.g1_compress(O.commit_known_secret(util.to_ints(scal), S))
     finally:
         ctx.set_option("heavy_cap", 1024)
+    # affine halving rounds before the accumulate kernel (msm_tree.cu), up to "every bucket down to one point"
+    for rounds in (1, 2, 3, 12):
+        ctx.set_option("msm_tree_rounds", rounds)
+        try:
+            assert ctx.msm_g1(st, scal) == O.g1_compress(O.commit_known_secret(util.to_ints(scal), S)), rounds
+        finally:
+            ctx.set_option("msm_tree_rounds", -1)
     # every threads-per-bucket split of the accumulate kernel / fused tail (T = 1 .. 32)
     for split in (0, 1, 2, 3, 5):
         ctx.set_option("acc_split", split)
