@@ -205,6 +205,31 @@ k_inv_top(Fq* __restrict__ v, uint64_t N) {
   st_fq(v + i, r);
 }
 
+// top of the tree, fused: u < U owns v[u + k U], k < 8 — prefix products in registers, ONE binary-GCD inversion,
+// back-substitution.  Replaces two levels + a per-value inversion kernel (five launches of pure latency).
+__global__ void __launch_bounds__(64)
+k_inv_top8(Fq* __restrict__ v, uint64_t N, uint64_t U) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  Fq x[INV_FAN], pf[INV_FAN];
+  Fq acc; set_one(acc);
+  int kmax = 0;
+#pragma unroll
+  for (int k = 0; k < INV_FAN; k++) {
+    const uint64_t idx = u + (uint64_t)k * U;
+    if (idx < N) { ld_fq_plain(x[k], v + idx); pf[k] = acc; mul(acc, acc, x[k]); kmax = k + 1; }
+  }
+  Fq inv; inv_gcd(inv, acc);
+#pragma unroll
+  for (int k = INV_FAN - 1; k >= 0; k--) {
+    if (k < kmax) {
+      Fq r; mul(r, inv, pf[k]);
+      mul(inv, inv, x[k]);
+      st_fq(v + u + (uint64_t)k * U, r);
+    }
+  }
+}
+
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // scratch needed by batch_invert_inplace for N values, in Fq elements
@@ -228,7 +253,12 @@ int32_t batch_invert_inplace(kzg_ctx* ctx, Fq* v, uint64_t N, Fq* ws, uint64_t t
     KZG_LAUNCHED(ctx);
     cur = l.up; n = U;
   }
-  k_inv_top<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(cur, n);
+  if (n > 64) {
+    const uint64_t U = (n + INV_FAN - 1) / INV_FAN;
+    k_inv_top8<<<blocks_for(U, 64), 64, 0, ctx->stream>>>(cur, n, U);
+  } else {
+    k_inv_top<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(cur, n);
+  }
   KZG_LAUNCHED(ctx);
   for (int i = nl - 1; i >= 0; i--) {
     k_inv_down<<<blocks_for(lv[i].U, 128), 128, 0, ctx->stream>>>(lv[i].v, lv[i].N, lv[i].U, lv[i].pf, lv[i].up);
@@ -266,7 +296,7 @@ int32_t msm_fixed_batch_tree(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* sc
   if (W > 32) return fail(ctx, KZG_E_BAD_ARG, "tree path needs window_bits >= 8");
   const uint64_t KP = (uint64_t)(W + 1) / 2;
   const uint64_t chunk = (uint64_t)ctx->opt_tree_chunk_rows > 0 ? (uint64_t)ctx->opt_tree_chunk_rows : 2048;
-  const uint64_t top = 8192;   // values left for the inversion kernel
+  const uint64_t top = (uint64_t)ctx->opt_inv_top;   // values left for the fused top kernel (8 per thread)
   const uint64_t rows_max = rows_total < chunk ? rows_total : chunk;
   const uint64_t pts1 = rows_max * n * KP;             // points after round 1
   void *A, *B, *PF, *TW;

@@ -15,27 +15,47 @@ namespace kzg {
 
 constexpr int ST_K = 8;          // consecutive output points per thread
 
-// seg_out[b] = sum_{b' < b} ceil(len(b') / 2), b = 0 .. M  (one block)
+// bucket bounds of every round at once: with len_0(b) = seg0[b+1] - seg0[b] and len_r = ceil(len_{r-1} / 2),
+// segs[r][b] = sum_{b' < b} len_{r+1}(b'), b = 0 .. M, r < R.  One block; a thread owns a contiguous range of
+// buckets (its lengths stay in registers / L1 across the rounds), block-wide scan of the range totals per round.
 __global__ void __launch_bounds__(1024)
-k_seg_scan(const uint32_t* __restrict__ seg_in, uint32_t M, uint32_t* __restrict__ seg_out) {
+k_seg_scan_all(const uint32_t* __restrict__ seg0, uint32_t M, int R, uint32_t* __restrict__ segs) {
   __shared__ uint32_t sh[1024];
   const uint32_t tid = threadIdx.x;
   const uint32_t per = (M + 1023) / 1024;
   const uint32_t lo = tid * per < M ? tid * per : M;
   const uint32_t hi = lo + per < M ? lo + per : M;
-  uint32_t sum = 0;
-  for (uint32_t b = lo; b < hi; b++) sum += (seg_in[b + 1] - seg_in[b] + 1) >> 1;
-  sh[tid] = sum;
-  __syncthreads();
-  for (uint32_t d = 1; d < 1024; d <<= 1) {
-    uint32_t v = tid >= d ? sh[tid - d] : 0;
+  for (int r = 0; r < R; r++) {
+    uint32_t* out = segs + (size_t)r * (M + 2);
+    uint32_t sum = 0;
+    uint32_t prev = lo < hi ? __ldg(seg0 + lo) : 0;
+#pragma unroll 8
+    for (uint32_t b = lo; b < hi; b++) {
+      uint32_t nx = __ldg(seg0 + b + 1);
+      uint32_t len = nx - prev; prev = nx;
+      for (int q = 0; q <= r; q++) len = (len + 1) >> 1;
+      sum += len;
+    }
     __syncthreads();
-    sh[tid] += v;
+    sh[tid] = sum;
     __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+      uint32_t v = tid >= d ? sh[tid - d] : 0;
+      __syncthreads();
+      sh[tid] += v;
+      __syncthreads();
+    }
+    uint32_t run = tid ? sh[tid - 1] : 0;
+    prev = lo < hi ? __ldg(seg0 + lo) : 0;
+#pragma unroll 8
+    for (uint32_t b = lo; b < hi; b++) {
+      uint32_t nx = __ldg(seg0 + b + 1);
+      uint32_t len = nx - prev; prev = nx;
+      for (int q = 0; q <= r; q++) len = (len + 1) >> 1;
+      out[b] = run; run += len;
+    }
+    if (tid == 1023) out[M] = sh[1023];
   }
-  uint32_t run = tid ? sh[tid - 1] : 0;
-  for (uint32_t b = lo; b < hi; b++) { seg_out[b] = run; run += (seg_in[b + 1] - seg_in[b] + 1) >> 1; }
-  if (tid == 1023) seg_out[M] = sh[1023];
 }
 
 __global__ void k_iota(uint32_t* out, uint64_t n) {
@@ -147,7 +167,7 @@ static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((
 int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const G1Affine* tab,
                         uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
                         const uint32_t** seg_out_p, const uint32_t** iota_out, uint64_t* entries_out) {
-  const uint64_t top = 8192;
+  const uint64_t top = (uint64_t)ctx->opt_inv_top;
   // upper bounds on the number of points after each round (exact counts stay on the device)
   auto halve = [M](uint64_t e) { uint64_t h = (e + M) / 2 + 1; return h < e ? h : e; };   // never grows
   const uint64_t e1 = halve(entries);
@@ -158,11 +178,13 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   KZG_TRY(scratch_get(ctx, SCR_TREE_B, e2 * sizeof(G1Affine), &B));
   KZG_TRY(scratch_get(ctx, SCR_TREE_PREFIX, (T1 * ST_K + 16) * sizeof(Fq), &PF));
   KZG_TRY(scratch_get(ctx, SCR_TREE_TOT, (T1 + invert_scratch_elems(T1, top)) * sizeof(Fq), &TW));
-  KZG_TRY(scratch_get(ctx, SCR_TREE_SEG, 2 * ((size_t)M + 2) * 4, &SG));
+  KZG_TRY(scratch_get(ctx, SCR_TREE_SEG, (size_t)rounds * ((size_t)M + 2) * 4, &SG));
   Fq* prefix = reinterpret_cast<Fq*>(PF);
   Fq* tot = reinterpret_cast<Fq*>(TW);
   Fq* inv_ws = tot + T1;
-  uint32_t* seg[2] = {reinterpret_cast<uint32_t*>(SG), reinterpret_cast<uint32_t*>(SG) + M + 2};
+  uint32_t* segs = reinterpret_cast<uint32_t*>(SG);
+  k_seg_scan_all<<<1, 1024, 0, ctx->stream>>>(start_dev, M, rounds, segs);
+  KZG_LAUNCHED(ctx);
   G1Affine* buf[2] = {reinterpret_cast<G1Affine*>(A), reinterpret_cast<G1Affine*>(B)};
 
   const uint32_t* seg_in = start_dev;
@@ -171,10 +193,8 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   for (int r = 0; r < rounds; r++) {
     bound = halve(bound);
     const uint64_t T = (bound + ST_K - 1) / ST_K;
-    uint32_t* so = seg[r & 1];
+    uint32_t* so = segs + (size_t)r * (M + 2);
     G1Affine* out = buf[r & 1];
-    k_seg_scan<<<1, 1024, 0, ctx->stream>>>(seg_in, M, so);
-    KZG_LAUNCHED(ctx);
     if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, prefix, tot);
     else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot);
     KZG_LAUNCHED(ctx);

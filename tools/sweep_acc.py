@@ -12,11 +12,11 @@ st = ctx.setup_generate(O.BENCH_SECRET_BE, n)
 st.prepare_msm(16)
 scal = util.scalar_stream_bytes(0xC3, n)
 exp = O.g1_compress(O.commit_known_secret(util.to_ints(scal), O.fr_from_be_bytes(O.BENCH_SECRET_BE)))
-for mb in (0, 1, 2, 3, 4):
-    for sp in (-1, 2, 3):
-        ctx.set_option("msm_tree_rounds", mb); ctx.set_option("acc_split", sp)
+for mb in (0, 3, 3, 3):
+    for sp in (1024, 8192, 65536, 262144):
+        ctx.set_option("msm_tree_rounds", mb); ctx.set_option("inv_top", sp)
         best = None
-        for rep in range(4):
+        for rep in range(8):
             got = ctx.msm_g1(st, scal)
             r = (ctx.last_kernel_ms(0), ctx.last_kernel_ms(1), got == exp)
             if rep and (best is None or r[0] < best[0]): best = r
