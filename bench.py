@@ -32,6 +32,9 @@ SEED = 0xC3
 MAC_PER_FQ_MUL = 300          # 12x12 product + 12x12+12 reduction
 MAC_PER_BUCKET_ADD = 3000     # XYZZ += affine: 8M + 2S = 10 Fq multiplications
 CANONICAL_MAC_PER_POINT = 48000  # c = 16: 16 windows x 3000 (SURVEY §8d canonical figure)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add<true> launch at n = 2^20, c = 16, from the
+# ncu --set full capture summarised in profiles/prof_seg_add_r01_summary.txt (bytes per launch)
+TRAFFIC_NCU = 3.728110e9 + 824.405248e6
 
 
 def _clock_sampler(stop, samples, device_index):
@@ -204,11 +207,12 @@ def run_ours(args):
     launches0 = ctx.launches
     ms_total, r_dev = timed(step_dev, args.steps)
     launches = ctx.launches - launches0
-    acc_ms = []
-    for _ in range(min(args.steps, 5)):   # per-launch duration of the dominant kernel, CUDA events on its stream
+    acc_ms, dom_ms = [], []
+    for _ in range(min(args.steps, 5)):   # per-launch durations, CUDA events on the stream the kernels run on
         step_dev()
         ctx.sync()
-        acc_ms.append(ctx.last_kernel_ms(0))
+        acc_ms.append(ctx.last_kernel_ms(0))   # accumulation phase (halving rounds + bucket accumulate)
+        dom_ms.append(ctx.last_kernel_ms(2))   # its dominant kernel
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     ms_e2e, r_e2e = timed(step_e2e, args.steps)
@@ -234,10 +238,15 @@ def run_ours(args):
         import math
         from ctypes import c_int
         acc = sorted(acc_ms)[len(acc_ms) // 2]
+        dom = sorted(dom_ms)[len(dom_ms) // 2]
         windows = setup_windows(ctx, setup, per, args.window)
-        adds = windows["W"] * per
-        achieved = adds * MAC_PER_BUCKET_ADD / (acc * 1e-3)
-        hbm_bytes = adds * 100  # 96 B affine point + 4 B sorted index per bucket addition
+        adds = windows["W"] * per                       # bucket additions of the whole phase
+        tree = adds >= (1 << 23)                        # msm_bucket's rule for the affine halving rounds
+        dom_adds = adds // 2 if tree else adds          # round 1 pairs up all entries: half of the additions
+        dom_name = "k_seg_add<true> (round-1 pair additions of the affine halving, msm_tree.cu)" if tree else "k_bucket_acc"
+        achieved = dom_adds * MAC_PER_BUCKET_ADD / (dom * 1e-3)
+        phase_achieved = adds * MAC_PER_BUCKET_ADD / (acc * 1e-3)
+        hbm_bytes = dom_adds * (2 * 96 + 2 * 4 + 48 + 96) if tree else adds * 100  # per pair: two table points, two indices, prefix in, point out
         threads = os.cpu_count() or 1
         cpu_points = min(1 << LOG_N, 49152 * threads)   # ~10 s of host work
         cpu_val, cpu_dt = cpu_baseline(cpu_points, threads) if world == 1 else (None, None)
@@ -255,16 +264,29 @@ def run_ours(args):
                     "d2h_bytes_per_step": 48, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": _clocks_summary(samples),
-            "roofline": {"bound": "int32-multiply (IMAD.WIDE), not hbm/tensor: MSM is integer-compute-bound",
-                         "kernel": "k_bucket_acc", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
-                         "unit": "T wide-MAC/s", "frac": achieved / imad_peak,
-                         "peak_source": "kzg_probe_imad_peak (independent mad.wide.u32 chains) in this run",
-                         "kernel_ms": acc, "kernel_share_of_step": acc / ms_step,
-                         "fq_mul_per_s_kernel": adds * 10 / (acc * 1e-3), "fq_mul_per_s_probe": fq_peak,
-                         "canonical_frac": (n_total / world) * CANONICAL_MAC_PER_POINT / (ms_step * 1e-3) / imad_peak,
-                         "traffic": None,
-                         "hbm": {"achieved": hbm_bytes / (acc * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                                 "frac": hbm_bytes / (acc * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peaks_src}},
+            "roofline": {
+                "bound": "int32-multiply (IMAD.WIDE), not hbm/tensor: MSM is integer-compute-bound",
+                "kernel": ("bucket accumulation = k_seg_den + batch inversion + k_seg_add (3 affine halving rounds, "
+                           "msm_tree.cu) + k_bucket_acc" if tree else "k_bucket_acc"),
+                "achieved": phase_achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-MAC/s",
+                "frac": phase_achieved / imad_peak,
+                "work": f"algorithmic: {adds} bucket additions x 3000 wide-MAC (XYZZ += affine = 10 Fq products, SURVEY 8d)",
+                "peak_source": "kzg_probe_imad_peak (independent mad.wide.u32 chains) in this run",
+                "kernel_ms": acc, "kernel_share_of_step": acc / ms_step,
+                "dominant_kernel": {
+                    "name": dom_name, "ms": dom, "share_of_step": dom / ms_step,
+                    "as_implemented": ("5 Fq products = 1500 wide-MAC per pair addition (denominators and the shared "
+                                       "inversion run in k_seg_den / k_inv_*)" if tree else "10 Fq products = 3000 wide-MAC per addition"),
+                    "achieved": dom_adds * (1500 if tree else 3000) / (dom * 1e-3) / 1e12,
+                    "frac": dom_adds * (1500 if tree else 3000) / (dom * 1e-3) / imad_peak,
+                    "hbm": {"achieved": hbm_bytes / (dom * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                            "frac": hbm_bytes / (dom * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peaks_src,
+                            "algorithmic_bytes": hbm_bytes}},
+                "fq_mul_per_s_probe": fq_peak,
+                "canonical_frac": (n_total / world) * CANONICAL_MAC_PER_POINT / (ms_step * 1e-3) / imad_peak,
+                "traffic": TRAFFIC_NCU if tree and world == 1 else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add<true> launch (the dominant "
+                                "kernel), profiles/prof_seg_add_r01_summary.txt"},
         }
         if blob is not None:
             line["blob_batch"] = blob

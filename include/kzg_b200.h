@@ -59,7 +59,9 @@ int32_t kzg_ctx_sync(kzg_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx);
 /* device time of the last bulk call's dominant kernel(s) in ms, measured with CUDA events on
- * the ctx stream: which = 0 bucket accumulate / fixed-base accumulate, 1 whole call */
+ * the ctx stream: which = 0 accumulation phase (affine halving rounds + bucket accumulate, or the fixed-base
+ * batch), 1 whole call, 2 the single dominant kernel (round-1 pair additions, or the bucket accumulate
+ * when the MSM is too small for the halving rounds) */
 float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which);
 /* CUDA-event stopwatch on the ctx stream (bench.py times its K-step region with it) */
 int32_t kzg_ctx_timer_start(kzg_ctx* ctx);

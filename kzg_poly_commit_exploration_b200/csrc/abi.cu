@@ -92,6 +92,7 @@ void update_timers(kzg_ctx* ctx) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[0] = ms;
   if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->last_ms[1] = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev_k[0], ctx->ev_k[1]) == cudaSuccess) ctx->last_ms[2] = ms;
   cudaGetLastError();
 }
 
@@ -114,6 +115,7 @@ int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id) {
   for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
   for (int i = 0; i < 4; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
   for (int i = 0; i < 2; i++) { cudaEventCreate(&ctx->ev_t[i]); cudaEventRecord(ctx->ev_t[i], ctx->stream); }
+  for (int i = 0; i < 2; i++) { cudaEventCreate(&ctx->ev_k[i]); cudaEventRecord(ctx->ev_k[i], ctx->stream); }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   cudaStreamSynchronize(ctx->stream);
@@ -131,6 +133,7 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
   if (ctx->g2table) cudaFree(ctx->g2table);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; i++) if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
+  for (int i = 0; i < 2; i++) if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -161,7 +164,7 @@ int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
 uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) { return ctx->launches; }
 
 float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which) {
-  return (which == 0 || which == 1) ? ctx->last_ms[which] : 0.f;
+  return (which >= 0 && which <= 2) ? ctx->last_ms[which] : 0.f;
 }
 
 int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {

@@ -28,7 +28,8 @@ struct kzg_ctx {
   std::string err;
   uint64_t launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  float last_ms[2] = {0.f, 0.f};
+  float last_ms[3] = {0.f, 0.f, 0.f};
+  cudaEvent_t ev_k[2] = {nullptr, nullptr};   // around the single dominant kernel of the last bulk call
   cudaEvent_t ev_t[2] = {nullptr, nullptr};
   void* scratch[kzg::SCR_COUNT] = {};
   size_t scratch_cap[kzg::SCR_COUNT] = {};

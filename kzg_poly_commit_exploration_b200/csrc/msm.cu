@@ -245,11 +245,13 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
     if (ctx->opt_acc_minblocks == 4) kern = k_bucket_acc<4>;
     else if (ctx->opt_acc_minblocks == 5) kern = k_bucket_acc<5>;
     else if (ctx->opt_acc_minblocks == 6) kern = k_bucket_acc<6>;
+    if (rounds == 0) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
     kern<<<blocks_for((uint64_t)half << logT, 128), 128, 0, ctx->stream>>>(
         acc_start, acc_vals, acc_tab, half, logT, heavy_cap,
         reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
   }
   KZG_LAUNCHED(ctx);
+  if (rounds == 0) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   {
     void* hp;

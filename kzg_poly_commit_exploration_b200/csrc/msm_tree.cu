@@ -199,8 +199,11 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
     else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot);
     KZG_LAUNCHED(ctx);
     KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
-    if (r == 0) k_seg_add<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, prefix, tot, out);
-    else k_seg_add<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot, out);
+    if (r == 0) {
+      KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
+      k_seg_add<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, prefix, tot, out);
+      KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
+    } else k_seg_add<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot, out);
     KZG_LAUNCHED(ctx);
     seg_in = so; src = out;
   }
