@@ -46,7 +46,7 @@ struct kzg_ctx {
   int opt_tree_chunk_rows = 2048;      // rows reduced together (bounds the scratch: ~8 KiB * n/4096 * W/2 per row... see DESIGN)
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
   int64_t opt_inv_top = 1 << 18;       // batch inversion: values left for the fused top kernel
-  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 from 2^23 entries)
+  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 above 2^23 entries)
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
 };

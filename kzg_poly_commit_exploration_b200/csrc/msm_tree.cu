@@ -7,7 +7,7 @@
 // trick across the grid, batch_tree.cu) — 6.6 products per addition.  Three rounds do 7/8 of all additions;
 // what is left (W*n/8 dense affine points, same bucket structure) goes to k_bucket_acc and the usual tail.
 // Only worth it when a round has millions of independent additions (its inversion chain is ~0.15 ms of
-// latency): msm_bucket enables it from 2^23 entries.  Pairs never cross a bucket; a run of odd length passes
+// latency; measured break-even at 2^23 entries, -13 % at 2^24): msm_bucket enables it above 2^23 entries.  Pairs never cross a bucket; a run of odd length passes
 // its last entry through; additions are complete (infinity, P = Q, P = -Q).
 #include "affine_tree.cuh"
 

@@ -6,13 +6,14 @@ import kzg_oracle as O
 import util
 import kzg_poly_commit_exploration_b200 as pkg
 
-n = 1 << 20
+logn = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+n = 1 << logn
 ctx = pkg.Context(0)
 st = ctx.setup_generate(O.BENCH_SECRET_BE, n)
 st.prepare_msm(16)
 scal = util.scalar_stream_bytes(0xC3, n)
 exp = O.g1_compress(O.commit_known_secret(util.to_ints(scal), O.fr_from_be_bytes(O.BENCH_SECRET_BE)))
-for mb in (0, 3, 3):
+for mb in (0, 1, 2, 3):
     for sp in (262144,):
         ctx.set_option("msm_tree_rounds", mb); ctx.set_option("inv_top", sp)
         best = None
