@@ -223,9 +223,10 @@ def run_ours(args):
 
     imad_peak = ctx.probe_imad_peak()
     fq_peak = ctx.probe_fq_mul()
+    setup.close()
+    extra = other_configs(ctx, synthetic, torch, dist, dev, world, rank)
     blob = None
     if args.blobs > 0:
-        setup.close()
         blob = blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, args.blobs, 2, args.fixed_window)
 
     if rank == 0:
@@ -288,6 +289,7 @@ def run_ours(args):
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add<true> launch (the dominant "
                                 "kernel), profiles/prof_seg_add_r01_summary.txt"},
         }
+        line["other_configs"] = extra
         if blob is not None:
             line["blob_batch"] = blob
         if cpu_val is not None:
@@ -295,11 +297,52 @@ def run_ours(args):
                                     "sample": f"{cpu_points}-point prefix of the same scalars, reference naive loop "
                                               f"(src/polynomial.rs:207-212) split over {threads} threads, {cpu_dt:.2f} s"}
         print(json.dumps(line))
-    if blob is None:
-        setup.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(ctx, synthetic, torch, dist, dev, world, rank):
+    """BASELINE configs C5 (powers-of-tau generation of 2^22 G1 points, sharded by index range) and C2 (degree
+    2^16 commit + evaluate + open on one GPU), timed once each beside the headline; parity for both is in tests/."""
+    out = {}
+    n5 = 1 << 22
+    per = n5 // world
+    st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, 1 << 12)   # builds the generator table (once per ctx)
+    st.close()
+    if world > 1:
+        dist.barrier()
+    ctx.sync()
+    t0 = time.perf_counter()
+    st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, per, first=rank * per)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    t0 = time.perf_counter()
+    st.generate_g2(synthetic.BENCH_SECRET_BE, 1 << 16)
+    ctx.sync()
+    dt_g2 = time.perf_counter() - t0
+    st.close()
+    out["setup_2^22_g1"] = {"metric": "setup_points_per_s", "value": n5 / dt, "unit": "G1 points/s", "ms": dt * 1e3,
+                            "sharding": f"index range, {per} points/GPU", "wide_mac_per_point": 48000,
+                            "g2_points_per_s_per_gpu": (1 << 16) / dt_g2}
+    if world == 1:
+        n2 = (1 << 16) + 1
+        st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, n2)
+        st.prepare_msm(0)
+        co = torch.from_numpy(synthetic.scalar_stream(0xC2, n2)).pin_memory()
+        z = synthetic.scalar_stream(0xC2F, 1).tobytes()
+        ctx.commit(st, co.data_ptr(), n2); ctx.open(st, co.data_ptr(), z, None, n2)
+        t0 = time.perf_counter(); ctx.commit(st, co.data_ptr(), n2); t_commit = time.perf_counter() - t0
+        t0 = time.perf_counter(); ctx.open(st, co.data_ptr(), z, None, n2); t_open = time.perf_counter() - t0
+        t0 = time.perf_counter(); ctx.evaluate(co.data_ptr(), z, n2); t_eval = time.perf_counter() - t0
+        st.close()
+        out["degree_2^16"] = {"commit_ms": t_commit * 1e3, "evaluate_ms": t_eval * 1e3, "open_ms": t_open * 1e3,
+                              "note": "host buffers through the C ABI (H2D + D2H inside), one polynomial, 1 GPU"}
+    return out
 
 
 def blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, blobs_total, steps, fixed_window):

@@ -127,7 +127,7 @@ k_batch_affine(const G1Xyzz* __restrict__ in, uint64_t n, G1Affine* __restrict__
     if (!is_zero(in[i].zz)) { Fq z = in[i].zzz; mul(acc, acc, z); }
     last = i;
   }
-  Fq ai; inv(ai, acc);
+  Fq ai; inv_gcd(ai, acc);
   for (uint64_t i = last;; i -= T) {
     G1Xyzz p = in[i];
     if (is_inf(p)) {
