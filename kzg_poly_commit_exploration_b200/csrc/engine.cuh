@@ -47,6 +47,8 @@ struct kzg_ctx {
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
   int64_t opt_inv_top = 1 << 18;       // batch inversion: values left for the fused top kernel
   int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 above 2^23 entries)
+  int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this
+                                       // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
 };
