@@ -49,6 +49,7 @@ struct kzg_ctx {
   int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 above 2^23 entries)
   int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
+  int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
 };

@@ -203,7 +203,181 @@ __global__ void k_set_inf_tail(G1Xyzz* out, uint32_t count) {
   if (i < count) { G1Xyzz p; set_inf(p); out[i] = p; }
 }
 
+// ---- 4-warp cooperative tail ---------------------------------------------------------------------------
+// A dependent XYZZ addition is 14 Fq products in sequence, but only 4 deep: u1,u2,s1,s2 | pp,rr,zz,zzz |
+// ppp,q,zz3 | t,s1ppp,zzz3.  In the tail nothing else can fill the machine, so the four warps of a block hold
+// IDENTICAL copies of one point per lane and each computes one product of the current stage; results travel
+// through 6 KB of shared memory.  An addition then costs 4 product latencies instead of 14, a doubling 3
+// instead of 9.  P = Q / P = -Q inside an addition (rare in the tail) fall back to the plain formula, decided
+// block-wide so that every thread meets the same barriers.
+struct CoopBuf { Fq v[4][32]; };
+
+__device__ __forceinline__ void coop_stage(Fq& r0, Fq& r1, Fq& r2, Fq& r3, const Fq& a0, const Fq& b0, const Fq& a1,
+                                           const Fq& b1, const Fq& a2, const Fq& b2, const Fq& a3, const Fq& b3,
+                                           CoopBuf* sh, uint32_t w, uint32_t lane) {
+  Fq x, y;
+  if (w == 0) { x = a0; y = b0; } else if (w == 1) { x = a1; y = b1; } else if (w == 2) { x = a2; y = b2; } else { x = a3; y = b3; }
+  Fq pr; mul(pr, x, y);
+  sh->v[w][lane] = pr;
+  __syncthreads();
+  r0 = sh->v[0][lane]; r1 = sh->v[1][lane]; r2 = sh->v[2][lane]; r3 = sh->v[3][lane];
+  __syncthreads();
+}
+
+// a += b (every warp of the block calls this with the same per-lane operands)
+__device__ __noinline__ void add4(G1Xyzz& a, const G1Xyzz& b, bool active, CoopBuf* sh, uint32_t w, uint32_t lane) {
+  const bool inf_a = is_inf(a), inf_b = is_inf(b);
+  Fq u1, u2, s1, s2, p, r, pp, rr, zz12, zzz12, ppp, q, zz3, zzz3, t, s1p, dummy;
+  coop_stage(u1, u2, s1, s2, a.x, b.zz, b.x, a.zz, a.y, b.zzz, b.y, a.zzz, sh, w, lane);
+  sub(p, u2, u1);
+  sub(r, s2, s1);
+  // lanes whose result is discarded (shuffles past the end of the warp hand a lane its own value) must not
+  // drag the block into the slow path
+  const bool special = active && !inf_a && !inf_b && is_zero(p);
+  coop_stage(pp, rr, zz12, zzz12, p, p, r, r, a.zz, b.zz, a.zzz, b.zzz, sh, w, lane);
+  coop_stage(ppp, q, zz3, dummy, p, pp, u1, pp, zz12, pp, p, p, sh, w, lane);
+  Fq x3; sub(x3, rr, ppp); sub(x3, x3, q); sub(x3, x3, q);
+  Fq qx; sub(qx, q, x3);
+  coop_stage(t, s1p, zzz3, dummy, r, qx, s1, ppp, zzz12, ppp, p, p, sh, w, lane);
+  G1Xyzz res;
+  res.x = x3; sub(res.y, t, s1p); res.zz = zz3; res.zzz = zzz3;
+  if (__syncthreads_or(special ? 1 : 0)) {
+    G1Xyzz slow = a; add(slow, b);          // plain complete formula (doubling / cancellation)
+    if (special) res = slow;
+  }
+  if (inf_b) res = a;
+  else if (inf_a) res = b;
+  a = res;
+}
+
+// a = 2a
+__device__ __noinline__ void dbl4(G1Xyzz& a, CoopBuf* sh, uint32_t w, uint32_t lane) {
+  const bool inf_a = is_inf(a);
+  Fq u, v, xx, m, wv, sv, mm, zzn, t, wy, zzzn, dummy;
+  dbl(u, a.y);
+  coop_stage(v, xx, dummy, dummy, u, u, a.x, a.x, u, u, u, u, sh, w, lane);
+  dbl(m, xx); add(m, m, xx);
+  coop_stage(wv, sv, mm, zzn, u, v, a.x, v, m, m, v, a.zz, sh, w, lane);
+  Fq x3; sub(x3, mm, sv); sub(x3, x3, sv);
+  Fq sx; sub(sx, sv, x3);
+  coop_stage(t, wy, zzzn, dummy, m, sx, wv, a.y, wv, a.zzz, u, u, sh, w, lane);
+  if (!inf_a) { a.x = x3; sub(a.y, t, wy); a.zz = zzn; a.zzz = zzzn; }
+}
+
+__device__ __forceinline__ void coop_suffix_scan(G1Xyzz& R, CoopBuf* sh, uint32_t w, uint32_t lane) {
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    G1Xyzz o; shfl_down_pt(o, R, d);
+    G1Xyzz n = R; add4(n, o, lane + d < 32, sh, w, lane);
+    if (lane + d < 32) R = n;
+  }
+}
+__device__ __forceinline__ void coop_tree_sum(G1Xyzz& X, CoopBuf* sh, uint32_t w, uint32_t lane) {
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    G1Xyzz o; shfl_down_pt(o, X, d);
+    G1Xyzz n = X; add4(n, o, lane < d, sh, w, lane);
+    if (lane < d) X = n;
+  }
+}
+
+// level 1, cooperative: a block (4 warps) owns 32 consecutive buckets
+__global__ void __launch_bounds__(128)
+k_reduce_l1c(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* __restrict__ W_out,
+             G1Xyzz* __restrict__ S_out) {
+  __shared__ CoopBuf sh;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t b = blockIdx.x * 32 + lane;
+  G1Xyzz X; set_inf(X);
+  if (b < M) X = parts[(size_t)b * T];
+#pragma unroll 1
+  for (uint32_t k = 1; k < T; k++) {
+    G1Xyzz o; set_inf(o);
+    if (b < M) o = parts[(size_t)b * T + k];
+    add4(X, o, true, &sh, w, lane);
+  }
+  coop_suffix_scan(X, &sh, w, lane);
+  if (threadIdx.x == 0) S_out[blockIdx.x] = X;
+  if (lane == 0) set_inf(X);
+  coop_tree_sum(X, &sh, w, lane);
+  if (threadIdx.x == 0) W_out[blockIdx.x] = X;
+}
+
+// level 2, cooperative: block 2k runs the S chain of chunk k, block 2k+1 folds its W0 values
+__global__ void __launch_bounds__(128)
+k_reduce_l2c(const G1Xyzz* __restrict__ S0, const G1Xyzz* __restrict__ W0, uint32_t m,
+             G1Xyzz* __restrict__ S1, G1Xyzz* __restrict__ W1, G1Xyzz* __restrict__ V) {
+  __shared__ CoopBuf sh;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t k = blockIdx.x >> 1;
+  const uint32_t idx = k * 32 + lane;
+  G1Xyzz X;
+  if (blockIdx.x & 1) {
+    if (idx < m) X = W0[idx]; else set_inf(X);
+    coop_tree_sum(X, &sh, w, lane);
+    if (threadIdx.x == 0) V[k] = X;
+  } else {
+    if (idx < m) X = S0[idx]; else set_inf(X);
+    coop_suffix_scan(X, &sh, w, lane);
+    if (threadIdx.x == 0) S1[k] = X;
+    if (lane == 0) set_inf(X);
+    coop_tree_sum(X, &sh, w, lane);
+    if (threadIdx.x == 0) W1[k] = X;
+  }
+}
+
+// level 3, cooperative, three blocks: 0: S1 -> (S_total, W2); 1: sum W1; 2: sum V.  res[0..3] = S_total, W2, sumW1, sumV
+__global__ void __launch_bounds__(128)
+k_reduce_l3c(const G1Xyzz* __restrict__ S1, const G1Xyzz* __restrict__ W1, const G1Xyzz* __restrict__ V, uint32_t m2,
+             G1Xyzz* __restrict__ res) {
+  __shared__ CoopBuf sh;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const G1Xyzz* src = blockIdx.x == 0 ? S1 : (blockIdx.x == 1 ? W1 : V);
+  G1Xyzz X;
+  if (lane < m2) X = src[lane]; else set_inf(X);
+  if (blockIdx.x == 0) {
+    coop_suffix_scan(X, &sh, w, lane);
+    if (threadIdx.x == 0) res[0] = X;
+    if (lane == 0) set_inf(X);
+    coop_tree_sum(X, &sh, w, lane);
+    if (threadIdx.x == 0) res[1] = X;
+  } else {
+    coop_tree_sum(X, &sh, w, lane);
+    if (threadIdx.x == 0) res[blockIdx.x + 1] = X;
+  }
+}
+
+// Horner, cooperative: out = S_total + sumW0 + 32*(sumW1 + 32*(W2)), then the shallower pre-summed levels
+__global__ void __launch_bounds__(128)
+k_reduce_horner(const G1Xyzz* __restrict__ res, const G1Xyzz* __restrict__ pre, int npre, G1Xyzz* __restrict__ out) {
+  __shared__ CoopBuf sh;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  G1Xyzz acc = res[1];
+#pragma unroll 1
+  for (int l = 0; l < 2 + npre; l++) {
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) dbl4(acc, &sh, w, lane);
+    G1Xyzz t = l == 0 ? res[2] : (l == 1 ? res[3] : pre[npre - 1 - (l - 2)]);
+    add4(acc, t, true, &sh, w, lane);
+  }
+  G1Xyzz st = res[0];
+  add4(acc, st, true, &sh, w, lane);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// out[k] = sum of in[32k .. 32k+32), one cooperative block per output (few, latency-bound sums: the multi-GPU combine)
+__global__ void __launch_bounds__(128)
+k_sum_coop(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ out) {
+  __shared__ CoopBuf sh;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t idx = (uint64_t)blockIdx.x * 32 + lane;
+  G1Xyzz X;
+  if (idx < count) X = in[idx]; else set_inf(X);
+  coop_tree_sum(X, &sh, w, lane);
+  if (threadIdx.x == 0) out[blockIdx.x] = X;
+}
 
 int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev) {
   if (count == 0) {
@@ -221,7 +395,8 @@ int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* o
   while (true) {
     uint64_t chunks = (count + 31) / 32;
     G1Xyzz* dst = chunks == 1 ? out_dev : bufs[which];
-    k_sum_warp<<<blocks_for(chunks * 32, 128), 128, 0, ctx->stream>>>(src, count, dst);
+    if (chunks <= 64 && ctx->opt_coop_tail) k_sum_coop<<<(unsigned)chunks, 128, 0, ctx->stream>>>(src, count, dst);
+    else k_sum_warp<<<blocks_for(chunks * 32, 128), 128, 0, ctx->stream>>>(src, count, dst);
     KZG_LAUNCHED(ctx);
     if (chunks == 1) break;
     src = dst; count = chunks; which ^= 1;
@@ -236,7 +411,7 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
   void* ws;
   uint32_t shallow = 0;
   for (uint32_t m = M; m > 32768; m = (m + 31) / 32) shallow++;
-  size_t cap = (size_t)(M + 31) / 32 * 2 * 2 + 4096;
+  size_t cap = (size_t)(M + 31) / 32 * 2 * 2 + 4096 + 16;
   KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, cap * sizeof(G1Xyzz), &ws));
   G1Xyzz* pool = reinterpret_cast<G1Xyzz*>(ws);
   G1Xyzz* pre = pool; pool += 8;
@@ -267,6 +442,20 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
   G1Xyzz* S1 = pool; pool += m2;
   G1Xyzz* W1 = pool; pool += m2;
   G1Xyzz* V = pool; pool += m2;
+  if (ctx->opt_coop_tail) {
+    G1Xyzz* res = pool; pool += 4;
+    // level 1 stays one warp per chunk: all M/32 chains are resident at once, which four warps per chunk are not
+    if (ctx->opt_coop_tail == 2) k_reduce_l1c<<<m1, 128, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
+    else k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
+    KZG_LAUNCHED(ctx);
+    k_reduce_l2c<<<m2 * 2, 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V);
+    KZG_LAUNCHED(ctx);
+    k_reduce_l3c<<<3, 128, 0, ctx->stream>>>(S1, W1, V, m2, res);
+    KZG_LAUNCHED(ctx);
+    k_reduce_horner<<<1, 128, 0, ctx->stream>>>(res, pre, (int)shallow, result_dev);
+    KZG_LAUNCHED(ctx);
+    return KZG_OK;
+  }
   k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
   k_reduce_l2<<<blocks_for((uint64_t)m2 * 64, 128), 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V);
   KZG_LAUNCHED(ctx);
