@@ -236,7 +236,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   // threads per bucket: aim for ~2^18 accumulate threads
   uint32_t logT = 0;
   if (ctx->opt_acc_split >= 0) logT = (uint32_t)ctx->opt_acc_split;
-  else while ((half << logT) < (1u << 18) && (acc_entries >> (c - 1 + logT)) > (uint64_t)(rounds > 0 ? 4 : ctx->opt_acc_min_entries)) logT++;
+  else while ((half << logT) < (1u << 18) && (acc_entries >> (c - 1 + logT)) > (uint64_t)(rounds > 0 ? 8 : ctx->opt_acc_min_entries)) logT++;
   const uint32_t T = 1u << logT;
   void* parts = bk;
   if (logT) KZG_TRY(scratch_get(ctx, SCR_PARTIALS, ((size_t)half << logT) * sizeof(G1Xyzz), &parts));

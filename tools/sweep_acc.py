@@ -16,11 +16,11 @@ exp = O.g1_compress(O.commit_known_secret(util.to_ints(scal), O.fr_from_be_bytes
 cs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [16]
 for mb in cs:
     st.prepare_msm(mb)
-    for sp in (32, 16, 8, 4):
-        ctx.set_option("acc_min_entries", sp)
+    for sp in (-1, 1, 2, 3, 4):
+        ctx.set_option("acc_split", sp)
         best = None
         for rep in range(8):
             got = ctx.msm_g1(st, scal)
             r = (ctx.last_kernel_ms(0), ctx.last_kernel_ms(1), got == exp)
             if rep and (best is None or r[0] < best[0]): best = r
-        print(f"c={mb} acc_min_entries={sp}: acc {best[0]:.3f} ms  total-dev {best[1]:.3f} ms  dominant kernel {ctx.last_kernel_ms(2):.3f} ms ok={best[2]}", flush=True)
+        print(f"c={mb} acc_split={sp}: acc {best[0]:.3f} ms  total-dev {best[1]:.3f} ms  dominant kernel {ctx.last_kernel_ms(2):.3f} ms ok={best[2]}", flush=True)
