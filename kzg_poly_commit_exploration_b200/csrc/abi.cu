@@ -112,6 +112,8 @@ int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id) {
   ctx->device = device_id;
   if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
+  for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
   for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
   for (int i = 0; i < 4; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
   for (int i = 0; i < 2; i++) { cudaEventCreate(&ctx->ev_t[i]); cudaEventRecord(ctx->ev_t[i], ctx->stream); }
@@ -134,6 +136,8 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; i++) if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
   for (int i = 0; i < 2; i++) if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+  for (int i = 0; i < 8; i++) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -502,6 +506,12 @@ int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_
   return KZG_OK;
 }
 
+// rows per host->device staging chunk of a batch call: the tree path's chunk for large batches, else everything
+static uint64_t batch_chunk_rows(const kzg_ctx* ctx, uint64_t blobs) {
+  const uint64_t c = ctx->opt_tree_chunk_rows > 0 ? (uint64_t)ctx->opt_tree_chunk_rows : 2048;
+  return (blobs >= 2 * c && blobs >= (uint64_t)ctx->opt_tree_min_rows) ? c : blobs;
+}
+
 static uint64_t batch_max_trimmed(const uint8_t* coeffs, uint64_t blobs, uint64_t n) {
   uint64_t m = 0;
   for (uint64_t b = 0; b < blobs; b++) m = std::max(m, trimmed_len(coeffs + b * n * 32, n));
@@ -519,8 +529,19 @@ int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs
   void *d, *o;
   KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(blobs * n, 1) * 32, &d));
   KZG_TRY(scratch_get(ctx, SCR_OUT, blobs * 48, &o));
-  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, blobs * n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  KZG_TRY(kzg_commit_batch_dev(ctx, s, d, blobs, n, o));
+  // chunks of rows: the copy of chunk k+1 (copy stream) overlaps the reduction of chunk k (main stream)
+  const uint64_t chunk = batch_chunk_rows(ctx, blobs);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));          // scratch of earlier calls is free
+  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
+  uint64_t k = 0;
+  for (uint64_t r0 = 0; r0 < blobs; r0 += chunk, k++) {
+    const uint64_t rows = std::min(chunk, blobs - r0);
+    uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
+    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k % 7], 0));
+    KZG_TRY(kzg_commit_batch_dev(ctx, s, dc, rows, n, reinterpret_cast<uint8_t*>(o) + r0 * 48));
+  }
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c48, o, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   update_timers(ctx);
@@ -538,9 +559,19 @@ int32_t kzg_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_l
   KZG_TRY(scratch_get(ctx, SCR_FR_A, blobs * 64, &zy));
   uint8_t* zd = reinterpret_cast<uint8_t*>(zy);
   uint8_t* yd = zd + blobs * 32;
-  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, blobs * n * 32, cudaMemcpyHostToDevice, ctx->stream));
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le32, blobs * 32, cudaMemcpyHostToDevice, ctx->stream));
-  KZG_TRY(kzg_open_batch_dev(ctx, s, d, blobs, n, zd, yd, o));
+  const uint64_t chunk = batch_chunk_rows(ctx, blobs);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
+  uint64_t k = 0;
+  for (uint64_t r0 = 0; r0 < blobs; r0 += chunk, k++) {
+    const uint64_t rows = std::min(chunk, blobs - r0);
+    uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
+    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k % 7], 0));
+    KZG_TRY(kzg_open_batch_dev(ctx, s, dc, rows, n, zd + r0 * 32, yd + r0 * 32, reinterpret_cast<uint8_t*>(o) + r0 * 48));
+  }
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le32, yd, blobs * 32, cudaMemcpyDeviceToHost, ctx->stream));
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(proofs_c48, o, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

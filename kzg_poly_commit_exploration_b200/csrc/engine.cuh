@@ -25,6 +25,8 @@ enum ScratchSlot {
 struct kzg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host->device staging of batch chunks, overlapped with compute on `stream`
+  cudaEvent_t ev_copy[8] = {};
   std::string err;
   uint64_t launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
