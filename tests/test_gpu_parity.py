@@ -449,3 +449,76 @@ def test_config_c2_degree_65536(ctx):
     assert int.from_bytes(y, "little") == O.horner(co, z)
     assert pr == O.g1_compress(O.proof_known_secret(co, S, z))
     st.close()
+
+
+# ---- BASELINE config C3 at full size: n = 2^20 through the shipped path (3 affine halving rounds) ----------
+def test_config_c3_msm_2_20(ctx):
+    n = 1 << 20
+    st = ctx.setup_generate(SECRET, n)
+    scal = util.scalar_stream_bytes(0xC3, n)
+    ints = util.to_ints(scal)
+    expect = O.g1_compress(O.commit_known_secret(ints, S))
+    got = ctx.msm_g1(st, scal)
+    assert got == expect
+    # same result without the halving rounds and without the cooperative tail (independent code paths)
+    for name, val in (("msm_tree_rounds", 0), ("coop_tail", 0)):
+        ctx.set_option(name, val)
+    try:
+        assert ctx.msm_g1(st, scal) == expect
+    finally:
+        ctx.set_option("msm_tree_rounds", -1); ctx.set_option("coop_tail", 1)
+    # linearity: MSM(a) + MSM(b) == MSM(a + b) on the same bases
+    other = util.scalar_stream_bytes(0x3C, n)
+    summed = util.from_ints([(x + y) % O.R for x, y in zip(ints, util.to_ints(other))])
+    import ctypes as C
+    L = native_lib()
+    o = (C.c_uint8 * 48)()
+    b48 = lambda x: (C.c_uint8 * 48).from_buffer_copy(x)
+    assert L.kzg_g1_add(b48(got), b48(ctx.msm_g1(st, other)), o) == 0
+    assert bytes(o) == ctx.msm_g1(st, summed)
+    st.close()
+
+
+def native_lib():
+    import kzg_poly_commit_exploration_b200 as pkg
+    return pkg.lib()
+
+
+# ---- BASELINE config C4 shape through the DEFAULT dispatch (>= 512 rows: affine tree, chunked) ---------------------
+def test_config_c4_batch_default_path(ctx):
+    import ctypes as C
+    n, blobs = 512, 1100
+    st = ctx.setup_generate(SECRET, n)
+    st.prepare_fixed(n, 13)
+    coeffs = util.scalar_stream_bytes(0xC4, blobs * n)
+    zs = util.scalar_stream_bytes(0xC4F, blobs)
+    ctx.set_option("tree_chunk_rows", 400)            # 3 chunks, the last one ragged
+    try:
+        commits = ctx.commit_batch(st, coeffs, blobs, n)
+        ys, proofs = ctx.open_batch(st, coeffs, blobs, n, zs)
+    finally:
+        ctx.set_option("tree_chunk_rows", 2048)
+    for b in (0, 1, 399, 400, 401, 799, 800, blobs - 1):
+        co = util.to_ints(coeffs[b * n * 32: (b + 1) * n * 32])
+        z = int.from_bytes(zs[32 * b: 32 * b + 32], "little")
+        assert commits[48 * b: 48 * b + 48] == O.g1_compress(O.commit_known_secret(co, S)), b
+        assert int.from_bytes(ys[32 * b: 32 * b + 32], "little") == O.horner(co, z), b
+        assert proofs[48 * b: 48 * b + 48] == O.g1_compress(O.proof_known_secret(co, S, z)), b
+    # checksum of checksums: the sum of all commitments is the commitment of the coefficient-wise sum,
+    # computed by the single-polynomial bucket MSM (a different kernel path)
+    import numpy as np
+    L = native_lib()
+    acc = O.g1_compress(None)
+    o = (C.c_uint8 * 48)()
+    b48 = lambda x: (C.c_uint8 * 48).from_buffer_copy(x)
+    for b in range(blobs):
+        assert L.kzg_g1_add(b48(acc), b48(commits[48 * b: 48 * b + 48]), o) == 0
+        acc = bytes(o)
+    tot = [0] * n
+    allc = util.to_ints(coeffs)
+    for b in range(blobs):
+        row = allc[b * n: (b + 1) * n]
+        tot = [(x + y) % O.R for x, y in zip(tot, row)]
+    st2 = ctx.setup_generate(SECRET, n)
+    assert ctx.msm_g1(st2, util.from_ints(tot)) == acc
+    st.close(); st2.close()
