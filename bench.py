@@ -154,22 +154,24 @@ def run_ours(args):
     scal_dev = host.to(dev)
     partial = torch.zeros(192, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(192 * world, dtype=torch.uint8, device=dev)
+    ext_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     torch.cuda.synchronize()
 
     def step_dev():
         if world == 1:
             return ctx.msm_g1_dev(setup, scal_dev.data_ptr(), per)
+        # partial MSM, NCCL all-gather of the 192-byte partials and the fold are enqueued in order on the
+        # engine's stream (torch sees it as an ExternalStream): no host synchronisation until the 48-byte result
         ctx.msm_g1_partial_dev(setup, scal_dev.data_ptr(), per, partial.data_ptr())
-        ctx.sync()
-        dist.all_gather_into_tensor(gathered, partial)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(ext_stream):
+            dist.all_gather_into_tensor(gathered, partial)
         return ctx.g1_combine_dev(gathered.data_ptr(), world)
 
     def step_e2e():
         if world == 1:
             return ctx.msm_g1(setup, host.data_ptr(), per)
-        scal_dev.copy_(host, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(ext_stream):
+            scal_dev.copy_(host, non_blocking=True)
         return step_dev()
 
     def barrier():

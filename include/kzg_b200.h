@@ -56,6 +56,9 @@ const char* kzg_last_error(const kzg_ctx* ctx);
 const char* kzg_status_string(int32_t status);
 /* block until all work queued on the ctx stream has finished */
 int32_t kzg_ctx_sync(kzg_ctx* ctx);
+/* the ctx's cudaStream_t: lets a host enqueue its own work (e.g. the NCCL all-gather of the partial sums,
+ * through torch.cuda.ExternalStream) in order with the engine's kernels instead of synchronising the host */
+void* kzg_ctx_stream(const kzg_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx);
 /* device time of the last bulk call's dominant kernel(s) in ms, measured with CUDA events on

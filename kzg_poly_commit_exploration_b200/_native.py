@@ -28,6 +28,7 @@ SIGNATURES = {
     "kzg_status_string": (C.c_char_p, [_i32]),
     "kzg_ctx_sync": (_i32, [_vp]),
     "kzg_ctx_launch_count": (_u64, [_vp]),
+    "kzg_ctx_stream": (_vp, [_vp]),
     "kzg_ctx_last_kernel_ms": (C.c_float, [_vp, _i32]),
     "kzg_ctx_timer_start": (_i32, [_vp]),
     "kzg_ctx_timer_stop": (_i32, [_vp, C.POINTER(C.c_float)]),

@@ -167,6 +167,8 @@ int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
 
 uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) { return ctx->launches; }
 
+void* kzg_ctx_stream(const kzg_ctx* ctx) { return ctx ? reinterpret_cast<void*>(ctx->stream) : nullptr; }
+
 float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which) {
   return (which >= 0 && which <= 2) ? ctx->last_ms[which] : 0.f;
 }

@@ -46,6 +46,11 @@ class Context:
         self.check(N.lib().kzg_ctx_sync(self._h))
 
     @property
+    def stream(self) -> int:
+        """cudaStream_t of this context (an int), e.g. for torch.cuda.ExternalStream."""
+        return int(N.lib().kzg_ctx_stream(self._h) or 0)
+
+    @property
     def launches(self) -> int:
         return int(N.lib().kzg_ctx_launch_count(self._h))
 
