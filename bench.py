@@ -244,7 +244,8 @@ def run_ours(args):
         dom = sorted(dom_ms)[len(dom_ms) // 2]
         windows = setup_windows(ctx, setup, per, args.window)
         adds = windows["W"] * per                       # bucket additions of the whole phase
-        tree = adds > (1 << 23)                         # msm_bucket's rule for the affine halving rounds
+        tree = adds >= (1 << 21)                        # msm_bucket's rule for the affine halving rounds
+        rounds = 3 if adds >= (1 << 23) else 2 if adds >= (1 << 22) else 1 if tree else 0
         dom_adds = adds // 2 if tree else adds          # round 1 pairs up all entries: half of the additions
         dom_name = "k_seg_add<true> (round-1 pair additions of the affine halving, msm_tree.cu)" if tree else "k_bucket_acc"
         achieved = dom_adds * MAC_PER_BUCKET_ADD / (dom * 1e-3)
@@ -269,7 +270,7 @@ def run_ours(args):
             "clocks": _clocks_summary(samples),
             "roofline": {
                 "bound": "int32-multiply (IMAD.WIDE), not hbm/tensor: MSM is integer-compute-bound",
-                "kernel": ("bucket accumulation = k_seg_den + batch inversion + k_seg_add (3 affine halving rounds, "
+                "kernel": (f"bucket accumulation = k_seg_den + batch inversion + k_seg_add ({rounds} affine halving rounds, "
                            "msm_tree.cu) + k_bucket_acc" if tree else "k_bucket_acc"),
                 "achieved": phase_achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-MAC/s",
                 "frac": phase_achieved / imad_peak,

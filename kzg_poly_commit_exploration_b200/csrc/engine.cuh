@@ -48,7 +48,7 @@ struct kzg_ctx {
   int opt_tree_chunk_rows = 2048;      // rows reduced together (bounds the scratch: ~8 KiB * n/4096 * W/2 per row... see DESIGN)
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
   int64_t opt_inv_top = 1 << 18;       // batch inversion: values left for the fused top kernel
-  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 above 2^23 entries)
+  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 / 2 / 1 from 2^23 / 2^22 / 2^21 entries)
   int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail

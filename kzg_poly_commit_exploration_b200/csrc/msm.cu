@@ -227,7 +227,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   const uint32_t* acc_vals = reinterpret_cast<uint32_t*>(vb);
   const G1Affine* acc_tab = s->msm_tab;
   uint64_t acc_entries = total;
-  int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : (total > (1ull << 23) ? 3 : 0)   /* measured: break-even at 2^23 entries */;
+  int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : (total >= (1ull << 23) ? 3 : total >= (1ull << 22) ? 2 : total >= (1ull << 21) ? 1 : 0)   /* measured, profiles/sweep_tree_rounds_r01.txt */;
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   if (rounds > 0)
     KZG_TRY(msm_tree_rounds(ctx, acc_start, acc_vals, acc_tab, half, total, rounds, &acc_tab, &acc_start, &acc_vals,

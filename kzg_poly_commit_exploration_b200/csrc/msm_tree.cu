@@ -7,7 +7,8 @@
 // trick across the grid, batch_tree.cu) — 6.6 products per addition.  Three rounds do 7/8 of all additions;
 // what is left (W*n/8 dense affine points, same bucket structure) goes to k_bucket_acc and the usual tail.
 // Only worth it when a round has millions of independent additions (its inversion chain is ~0.15 ms of
-// latency; measured break-even at 2^23 entries, -13 % at 2^24): msm_bucket enables it above 2^23 entries.  Pairs never cross a bucket; a run of odd length passes
+// latency): msm_bucket runs 3 rounds from 2^23 entries, 2 from 2^22, 1 from 2^21 (measured: -16 % at 2^24,
+// -11 % at 2^23, -9 % at 2^22, break-even at 2^21).  Pairs never cross a bucket; a run of odd length passes
 // its last entry through; additions are complete (infinity, P = Q, P = -Q).
 #include "affine_tree.cuh"
 
@@ -16,45 +17,70 @@ namespace kzg {
 constexpr int ST_K = 8;          // consecutive output points per thread
 
 // bucket bounds of every round at once: with len_0(b) = seg0[b+1] - seg0[b] and len_r = ceil(len_{r-1} / 2),
-// segs[r][b] = sum_{b' < b} len_{r+1}(b'), b = 0 .. M, r < R.  One block; a thread owns a contiguous range of
-// buckets (its lengths stay in registers / L1 across the rounds), block-wide scan of the range totals per round.
-__global__ void __launch_bounds__(1024)
-k_seg_scan_all(const uint32_t* __restrict__ seg0, uint32_t M, int R, uint32_t* __restrict__ segs) {
-  __shared__ uint32_t sh[1024];
-  const uint32_t tid = threadIdx.x;
-  const uint32_t per = (M + 1023) / 1024;
-  const uint32_t lo = tid * per < M ? tid * per : M;
-  const uint32_t hi = lo + per < M ? lo + per : M;
+// segs[r][b] = sum_{b' < b} len_{r+1}(b'), b = 0 .. M, r < R.  Three small launches (a single-block version took
+// 190 us of pure load latency): per-tile totals, scan of the tile totals, per-tile scans + offsets.
+constexpr int SEG_TILE = 1024;
+constexpr int SEG_MAX_ROUNDS = 16;
+
+__device__ __forceinline__ uint32_t halved(uint32_t len, int times) {
+  for (int q = 0; q < times; q++) len = (len + 1) >> 1;
+  return len;
+}
+// block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* sh /* 33 words */) {
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += t; }
+  if (lane == 31) sh[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = sh[lane], xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= (uint32_t)d) xi += t; }
+    sh[lane] = xi - x;                 // exclusive prefix of the warp totals
+    if (lane == 31) sh[32] = xi;
+  }
+  __syncthreads();
+  uint32_t res = sh[w] + inc - v;
+  *total = sh[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(SEG_TILE)
+k_seg_tile_sums(const uint32_t* __restrict__ seg0, uint32_t M, int R, uint32_t ntiles, uint32_t* __restrict__ tile_tot) {
+  __shared__ uint32_t sh[33];
+  const uint32_t b = blockIdx.x * SEG_TILE + threadIdx.x;
+  const uint32_t len0 = b < M ? __ldg(seg0 + b + 1) - __ldg(seg0 + b) : 0;
   for (int r = 0; r < R; r++) {
-    uint32_t* out = segs + (size_t)r * (M + 2);
-    uint32_t sum = 0;
-    uint32_t prev = lo < hi ? __ldg(seg0 + lo) : 0;
-#pragma unroll 8
-    for (uint32_t b = lo; b < hi; b++) {
-      uint32_t nx = __ldg(seg0 + b + 1);
-      uint32_t len = nx - prev; prev = nx;
-      for (int q = 0; q <= r; q++) len = (len + 1) >> 1;
-      sum += len;
-    }
-    __syncthreads();
-    sh[tid] = sum;
-    __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-      uint32_t v = tid >= d ? sh[tid - d] : 0;
-      __syncthreads();
-      sh[tid] += v;
-      __syncthreads();
-    }
-    uint32_t run = tid ? sh[tid - 1] : 0;
-    prev = lo < hi ? __ldg(seg0 + lo) : 0;
-#pragma unroll 8
-    for (uint32_t b = lo; b < hi; b++) {
-      uint32_t nx = __ldg(seg0 + b + 1);
-      uint32_t len = nx - prev; prev = nx;
-      for (int q = 0; q <= r; q++) len = (len + 1) >> 1;
-      out[b] = run; run += len;
-    }
-    if (tid == 1023) out[M] = sh[1023];
+    uint32_t tot;
+    block_excl_scan(halved(len0, r + 1), &tot, sh);
+    if (threadIdx.x == 0) tile_tot[(size_t)r * ntiles + blockIdx.x] = tot;
+  }
+}
+// one block: exclusive scan of the tile totals of every round (ntiles <= 1024), in place
+__global__ void __launch_bounds__(SEG_TILE)
+k_seg_tile_scan(uint32_t* __restrict__ tile_tot, uint32_t ntiles, int R, uint32_t M, uint32_t* __restrict__ segs) {
+  __shared__ uint32_t sh[33];
+  for (int r = 0; r < R; r++) {
+    uint32_t v = threadIdx.x < ntiles ? tile_tot[(size_t)r * ntiles + threadIdx.x] : 0;
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(v, &tot, sh);
+    if (threadIdx.x < ntiles) tile_tot[(size_t)r * ntiles + threadIdx.x] = ex;
+    if (threadIdx.x == 0) segs[(size_t)r * (M + 2) + M] = tot;
+  }
+}
+__global__ void __launch_bounds__(SEG_TILE)
+k_seg_write(const uint32_t* __restrict__ seg0, uint32_t M, int R, uint32_t ntiles, const uint32_t* __restrict__ tile_off,
+            uint32_t* __restrict__ segs) {
+  __shared__ uint32_t sh[33];
+  const uint32_t b = blockIdx.x * SEG_TILE + threadIdx.x;
+  const uint32_t len0 = b < M ? __ldg(seg0 + b + 1) - __ldg(seg0 + b) : 0;
+  for (int r = 0; r < R; r++) {
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(halved(len0, r + 1), &tot, sh);
+    if (b < M) segs[(size_t)r * (M + 2) + b] = ex + tile_off[(size_t)r * ntiles + blockIdx.x];
   }
 }
 
@@ -178,12 +204,20 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   KZG_TRY(scratch_get(ctx, SCR_TREE_B, e2 * sizeof(G1Affine), &B));
   KZG_TRY(scratch_get(ctx, SCR_TREE_PREFIX, (T1 * ST_K + 16) * sizeof(Fq), &PF));
   KZG_TRY(scratch_get(ctx, SCR_TREE_TOT, (T1 + invert_scratch_elems(T1, top)) * sizeof(Fq), &TW));
-  KZG_TRY(scratch_get(ctx, SCR_TREE_SEG, (size_t)rounds * ((size_t)M + 2) * 4, &SG));
+  if (rounds > SEG_MAX_ROUNDS) rounds = SEG_MAX_ROUNDS;
+  const uint32_t ntiles = (M + SEG_TILE - 1) / SEG_TILE;
+  if (ntiles > SEG_TILE) return fail(ctx, KZG_E_BAD_ARG, "too many buckets for the halving rounds");
+  KZG_TRY(scratch_get(ctx, SCR_TREE_SEG, (size_t)rounds * ((size_t)M + 2 + ntiles) * 4, &SG));
   Fq* prefix = reinterpret_cast<Fq*>(PF);
   Fq* tot = reinterpret_cast<Fq*>(TW);
   Fq* inv_ws = tot + T1;
   uint32_t* segs = reinterpret_cast<uint32_t*>(SG);
-  k_seg_scan_all<<<1, 1024, 0, ctx->stream>>>(start_dev, M, rounds, segs);
+  uint32_t* tile_tot = segs + (size_t)rounds * (M + 2);
+  k_seg_tile_sums<<<ntiles, SEG_TILE, 0, ctx->stream>>>(start_dev, M, rounds, ntiles, tile_tot);
+  KZG_LAUNCHED(ctx);
+  k_seg_tile_scan<<<1, SEG_TILE, 0, ctx->stream>>>(tile_tot, ntiles, rounds, M, segs);
+  KZG_LAUNCHED(ctx);
+  k_seg_write<<<ntiles, SEG_TILE, 0, ctx->stream>>>(start_dev, M, rounds, ntiles, tile_tot, segs);
   KZG_LAUNCHED(ctx);
   G1Affine* buf[2] = {reinterpret_cast<G1Affine*>(A), reinterpret_cast<G1Affine*>(B)};
 
