@@ -207,21 +207,22 @@ k_inv_top(Fq* __restrict__ v, uint64_t N) {
 
 // top of the tree, fused: u < U owns v[u + k U], k < 8 — prefix products in registers, ONE binary-GCD inversion,
 // back-substitution.  Replaces two levels + a per-value inversion kernel (five launches of pure latency).
+template <int F>
 __global__ void __launch_bounds__(64)
 k_inv_top8(Fq* __restrict__ v, uint64_t N, uint64_t U) {
   const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= U) return;
-  Fq x[INV_FAN], pf[INV_FAN];
+  Fq x[F], pf[F];
   Fq acc; set_one(acc);
   int kmax = 0;
 #pragma unroll
-  for (int k = 0; k < INV_FAN; k++) {
+  for (int k = 0; k < F; k++) {
     const uint64_t idx = u + (uint64_t)k * U;
     if (idx < N) { ld_fq_plain(x[k], v + idx); pf[k] = acc; mul(acc, acc, x[k]); kmax = k + 1; }
   }
   Fq inv; inv_gcd(inv, acc);
 #pragma unroll
-  for (int k = INV_FAN - 1; k >= 0; k--) {
+  for (int k = F - 1; k >= 0; k--) {
     if (k < kmax) {
       Fq r; mul(r, inv, pf[k]);
       mul(inv, inv, x[k]);
@@ -254,8 +255,13 @@ int32_t batch_invert_inplace(kzg_ctx* ctx, Fq* v, uint64_t N, Fq* ws, uint64_t t
     cur = l.up; n = U;
   }
   if (n > 64) {
-    const uint64_t U = (n + INV_FAN - 1) / INV_FAN;
-    k_inv_top8<<<blocks_for(U, 64), 64, 0, ctx->stream>>>(cur, n, U);
+    if (ctx->opt_inv_top_fan == 4) {
+      const uint64_t U = (n + 3) / 4;
+      k_inv_top8<4><<<blocks_for(U, 64), 64, 0, ctx->stream>>>(cur, n, U);
+    } else {
+      const uint64_t U = (n + INV_FAN - 1) / INV_FAN;
+      k_inv_top8<8><<<blocks_for(U, 64), 64, 0, ctx->stream>>>(cur, n, U);
+    }
   } else {
     k_inv_top<<<blocks_for(n, 64), 64, 0, ctx->stream>>>(cur, n);
   }

@@ -47,6 +47,7 @@ struct kzg_ctx {
   int opt_tree_min_rows = 512;         // batches of at least this many rows take the affine tree path (batch_tree.cu)
   int opt_tree_chunk_rows = 2048;      // rows reduced together (bounds the scratch: ~8 KiB * n/4096 * W/2 per row... see DESIGN)
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
+  int opt_inv_top_fan = 4;             // values per thread in the fused top kernel (4 or 8; measured: 4)
   int64_t opt_inv_top = 1 << 18;       // batch inversion: values left for the fused top kernel
   int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 / 2 / 1 from 2^23 / 2^22 / 2^21 entries)
   int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this

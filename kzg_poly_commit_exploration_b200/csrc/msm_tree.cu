@@ -14,7 +14,7 @@
 
 namespace kzg {
 
-constexpr int ST_K = 8;          // consecutive output points per thread
+constexpr int ST_K = 16;         // consecutive output points per thread
 
 // bucket bounds of every round at once: with len_0(b) = seg0[b+1] - seg0[b] and len_r = ceil(len_{r-1} / 2),
 // segs[r][b] = sum_{b' < b} len_{r+1}(b'), b = 0 .. M, r < R.  Three small launches (a single-block version took
