@@ -19,7 +19,7 @@
 
 namespace kzg {
 
-constexpr int TR_K = 8;            // pairs per thread in the generic rounds
+constexpr int TR_K = 16;           // pairs per thread in the generic rounds
 constexpr int TR_THREADS = 128;
 constexpr int INV_FAN = 8;         // fan-in of the batch-inversion product tree
 
