@@ -245,7 +245,7 @@ def run_ours(args):
         windows = setup_windows(ctx, setup, per, args.window)
         adds = windows["W"] * per                       # bucket additions of the whole phase
         tree = adds >= (1 << 21)                        # msm_bucket's rule for the affine halving rounds
-        rounds = 3 if adds >= (1 << 23) else 2 if adds >= (1 << 22) else 1 if tree else 0
+        rounds = max(0, min(6, adds.bit_length() - 21))   # msm.cu auto_tree_rounds
         dom_adds = adds // 2 if tree else adds          # round 1 pairs up all entries: half of the additions
         dom_name = "k_seg_add<true> (round-1 pair additions of the affine halving, msm_tree.cu)" if tree else "k_bucket_acc"
         achieved = dom_adds * MAC_PER_BUCKET_ADD / (dom * 1e-3)

@@ -49,7 +49,7 @@ struct kzg_ctx {
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
   int opt_inv_top_fan = 4;             // values per thread in the fused top kernel (4 or 8; measured: 4)
   int64_t opt_inv_top = 1 << 18;       // batch inversion: values left for the fused top kernel
-  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (3 / 2 / 1 from 2^23 / 2^22 / 2^21 entries)
+  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (log2(entries) - 20, 0..6)
   int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail

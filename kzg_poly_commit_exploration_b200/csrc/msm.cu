@@ -174,6 +174,14 @@ __global__ void k_set_inf(G1Xyzz* out, uint32_t count) {
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// affine halving rounds by problem size (measured, profiles/sweep_tree_rounds_r01.txt): one per doubling of the
+// entry count from 2^21 entries on — 1 at 2^21 (n = 2^17), 4 at 2^24 (n = 2^20), at most 6
+static int auto_tree_rounds(uint64_t entries) {
+  int r = 0;
+  while (r < 6 && (entries >> (21 + r)) != 0) r++;
+  return r;
+}
+
 int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
                    G1Xyzz* result_dev) {
   if (n == 0) {
@@ -227,7 +235,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   const uint32_t* acc_vals = reinterpret_cast<uint32_t*>(vb);
   const G1Affine* acc_tab = s->msm_tab;
   uint64_t acc_entries = total;
-  int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : (total >= (1ull << 23) ? 3 : total >= (1ull << 22) ? 2 : total >= (1ull << 21) ? 1 : 0)   /* measured, profiles/sweep_tree_rounds_r01.txt */;
+  int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds(total);
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   if (rounds > 0)
     KZG_TRY(msm_tree_rounds(ctx, acc_start, acc_vals, acc_tab, half, total, rounds, &acc_tab, &acc_start, &acc_vals,

@@ -7,8 +7,8 @@
 // trick across the grid, batch_tree.cu) — 6.6 products per addition.  Three rounds do 7/8 of all additions;
 // what is left (W*n/8 dense affine points, same bucket structure) goes to k_bucket_acc and the usual tail.
 // Only worth it when a round has millions of independent additions (its inversion chain is ~0.15 ms of
-// latency): msm_bucket runs 3 rounds from 2^23 entries, 2 from 2^22, 1 from 2^21 (measured: -16 % at 2^24,
-// -11 % at 2^23, -9 % at 2^22, break-even at 2^21).  Pairs never cross a bucket; a run of odd length passes
+// latency): msm_bucket runs one round per doubling of the entry count from 2^21 entries on (4 rounds at n = 2^20:
+// -18 %; break-even at 2^21).  Pairs never cross a bucket; a run of odd length passes
 // its last entry through; additions are complete (infinity, P = Q, P = -Q).
 #include "affine_tree.cuh"
 
