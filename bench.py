@@ -313,17 +313,23 @@ def other_configs(ctx, synthetic, torch, dist, dev, world, rank):
     per = n5 // world
     st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, 1 << 12)   # builds the generator table (once per ctx)
     st.close()
-    if world > 1:
-        dist.barrier()
-    ctx.sync()
-    t0 = time.perf_counter()
-    st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, per, first=rank * per)
-    ctx.sync()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dts = []
+    for rep in range(3):                      # the first pass also pays for the scratch allocations (~1.5 GB)
+        if rep:
+            st.close()
+        if world > 1:
+            dist.barrier()
+        ctx.sync()
+        t0 = time.perf_counter()
+        st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, per, first=rank * per)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        dts.append(dt)
+    dt = sorted(dts)[1]                       # median of 3
     t0 = time.perf_counter()
     st.generate_g2(synthetic.BENCH_SECRET_BE, 1 << 16)
     ctx.sync()
