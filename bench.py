@@ -433,7 +433,7 @@ def main():
     ap.add_argument("--window", type=int, default=int(os.environ.get("KZG_WINDOW", "0")))
     ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BLOBS", "4096")),
                     help="size of the secondary blob batch (0 = skip)")
-    ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "13")))
+    ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "15")))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -181,6 +181,7 @@ int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "acc_split") ctx->opt_acc_split = (int)value;
   else if (n == "acc_min_entries") ctx->opt_acc_min_entries = (int)std::max<int64_t>(1, value);
   else if (n == "coop_tail") ctx->opt_coop_tail = (int)value;
+  else if (n == "tree_k") ctx->opt_tree_k = (int)value;
   else if (n == "acc_minblocks") ctx->opt_acc_minblocks = (int)value;
   else if (n == "inv_top_fan") ctx->opt_inv_top_fan = (int)value;
   else if (n == "inv_top") ctx->opt_inv_top = std::max<int64_t>(8, value);

@@ -52,6 +52,7 @@ struct kzg_ctx {
   int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (log2(entries) - 20, 0..6)
   int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
+  int opt_tree_k = 0;                  // pairs per thread in the halving rounds: 0 = auto (fill the last wave), else 8..16
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;

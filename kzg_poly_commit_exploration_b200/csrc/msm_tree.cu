@@ -125,17 +125,17 @@ __device__ __forceinline__ PairRef pair_ref(const uint32_t* __restrict__ seg_in,
 template <bool R1>
 __global__ void __launch_bounds__(128)
 k_seg_den(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
-          const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T,
+          const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
           Fq* __restrict__ prefix, Fq* __restrict__ tot) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint32_t NP = __ldg(seg_out + M);
   Fq acc; set_one(acc);
-  const uint64_t p0 = t * ST_K;
+  const uint64_t p0 = t * K;
   if (p0 < NP) {
     uint32_t b = bucket_of(seg_out, M, (uint32_t)p0);
 #pragma unroll 1
-    for (int k = 0; k < ST_K; k++) {
+    for (int k = 0; k < K; k++) {
       const uint32_t p = (uint32_t)p0 + k;
       if (p >= NP) break;
       while (__ldg(seg_out + b + 1) <= p) b++;
@@ -152,12 +152,12 @@ k_seg_den(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_
 template <bool R1>
 __global__ void __launch_bounds__(128)
 k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
-          const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T,
+          const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
           const Fq* __restrict__ prefix, const Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint32_t NP = __ldg(seg_out + M);
-  const uint64_t p0 = t * ST_K;
+  const uint64_t p0 = t * K;
   if (p0 >= NP) return;
   uint32_t bk[ST_K];
   int kmax = 0;
@@ -165,7 +165,7 @@ k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_
     uint32_t b = bucket_of(seg_out, M, (uint32_t)p0);
     for (int k = 0; k < ST_K; k++) {
       const uint32_t p = (uint32_t)p0 + k;
-      if (p >= NP) break;
+      if (k >= K || p >= NP) break;
       while (__ldg(seg_out + b + 1) <= p) b++;
       bk[k] = b; kmax = k + 1;
     }
@@ -188,6 +188,7 @@ k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_
   }
 }
 
+
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
 int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const G1Affine* tab,
@@ -198,7 +199,7 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   auto halve = [M](uint64_t e) { uint64_t h = (e + M) / 2 + 1; return h < e ? h : e; };   // never grows
   const uint64_t e1 = halve(entries);
   const uint64_t e2 = halve(e1);
-  const uint64_t T1 = (e1 + ST_K - 1) / ST_K;
+  const uint64_t T1 = (e1 + 8 - 1) / 8;            // most threads a round can have (K >= 8)
   void *A, *B, *PF, *TW, *SG, *IO;
   KZG_TRY(scratch_get(ctx, SCR_TREE_A, e1 * sizeof(G1Affine), &A));
   KZG_TRY(scratch_get(ctx, SCR_TREE_B, e2 * sizeof(G1Affine), &B));
@@ -226,18 +227,29 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   uint64_t bound = entries;
   for (int r = 0; r < rounds; r++) {
     bound = halve(bound);
-    const uint64_t T = (bound + ST_K - 1) / ST_K;
+    // pairs per thread: the blocks of a launch are identical and run in lockstep, so a launch costs WHOLE waves of
+    // (4 blocks per SM) x K pair-times — 3.47 waves cost 4.  Pick the K <= 16 that fills the last wave.
+    int K = ST_K;
+    {
+      const double per_slot = (double)bound * 1.004 / ((double)ctx->sm_count * 4 * 128);
+      int waves = (int)((per_slot + ST_K - 1e-9) / ST_K); if (waves < 1) waves = 1;
+      K = (int)(per_slot / waves + 0.999999);
+      if (K < 8) K = 8;
+      if (K > ST_K) K = ST_K;
+      if (ctx->opt_tree_k >= 8 && ctx->opt_tree_k <= ST_K) K = ctx->opt_tree_k;
+    }
+    const uint64_t T = (bound + K - 1) / K;
     uint32_t* so = segs + (size_t)r * (M + 2);
     G1Affine* out = buf[r & 1];
-    if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, prefix, tot);
-    else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot);
+    if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot);
+    else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, K, prefix, tot);
     KZG_LAUNCHED(ctx);
     KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
     if (r == 0) {
       KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
-      k_seg_add<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, prefix, tot, out);
+      k_seg_add<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot, out);
       KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
-    } else k_seg_add<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, prefix, tot, out);
+    } else k_seg_add<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, K, prefix, tot, out);
     KZG_LAUNCHED(ctx);
     seg_in = so; src = out;
   }
