@@ -126,6 +126,15 @@ int32_t kzg_open(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, u
 int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n,
                    uint8_t out_c48[48]);
 
+/* the same call split in two, for callers that commit one polynomial after another (the reference's benches
+ * and CLI do: src/polynomial.rs:200-215 called in a loop): submit returns once the work is queued, wait blocks
+ * for the 48-byte result.  At most TWO tickets may be outstanding; the host->device copy of the newer call
+ * overlaps the kernels of the older one.  `scalars_le32` must stay valid (and should be page-locked for the copy
+ * to be asynchronous) until its ticket has been waited for. */
+int32_t kzg_msm_g1_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n,
+                          int32_t* ticket);
+int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]);
+
 /* ---- blob batches (BASELINE config C4): `blobs` polynomials of n coefficients each ------ */
 int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32,
                          uint64_t blobs, uint64_t n, uint8_t* out_c48);

@@ -131,6 +131,13 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < SCR_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (auto& q : ctx->pending) {
+    if (q.scalars) cudaFree(q.scalars);
+    if (q.result) cudaFree(q.result);
+    if (q.out_host) cudaFreeHost(q.out_host);
+    if (q.copied) cudaEventDestroy(q.copied);
+    if (q.done) cudaEventDestroy(q.done);
+  }
   if (ctx->gtable) cudaFree(ctx->gtable);
   if (ctx->g2table) cudaFree(ctx->g2table);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -357,6 +364,55 @@ int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32
   KZG_TRY(scratch_get(ctx, SCR_SCALARS, n * 32, &d));
   if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, scalars_le32, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   return kzg_msm_g1_dev(ctx, s, d, n, out_c48);
+}
+
+int32_t kzg_msm_g1_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket) {
+  if (!ctx || !s || (!scalars_le32 && n) || !ticket) return KZG_E_BAD_ARG;
+  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  DeviceGuard g(ctx->device);
+  const uint32_t t = ctx->next_ticket;
+  kzg_ctx::Pending& q = ctx->pending[t & 1];
+  if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "two calls are already in flight: wait for the older ticket first");
+  if (!q.copied) {
+    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.copied, cudaEventDisableTiming));
+    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+    KZG_CUDA_OK(ctx, cudaMalloc(&q.result, 512));
+    KZG_CUDA_OK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&q.out_host), 64, cudaHostAllocDefault));
+  }
+  const size_t bytes = n ? n * 32 : 32;
+  if (q.cap < bytes) {
+    if (q.scalars) { KZG_CUDA_OK(ctx, cudaFree(q.scalars)); q.scalars = nullptr; q.cap = 0; }
+    KZG_CUDA_OK(ctx, cudaMalloc(&q.scalars, bytes));
+    q.cap = bytes;
+  }
+  // the copy runs on the copy stream, beside whatever the engine stream is still computing
+  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+  KZG_CUDA_OK(ctx, cudaEventRecord(q.copied, ctx->copy_stream));
+  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, q.copied, 0));
+  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(q.result);
+  uint8_t* out_dev = reinterpret_cast<uint8_t*>(q.result) + 256;
+  KZG_TRY(msm_any(ctx, s, reinterpret_cast<const uint8_t*>(q.scalars), n, res));
+  KZG_TRY(finalize_points(ctx, res, 1, out_dev));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.out_host, out_dev, 48, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaEventRecord(q.done, ctx->stream));
+  q.busy = true;
+  *ticket = (int32_t)t;
+  ctx->next_ticket = t + 1;
+  return KZG_OK;
+}
+
+int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
+  if (!ctx || !out_c48 || ticket < 0) return KZG_E_BAD_ARG;
+  kzg_ctx::Pending& q = ctx->pending[(uint32_t)ticket & 1];
+  const uint32_t t = (uint32_t)ticket;
+  if (!q.busy || (t + 1 != ctx->next_ticket && t + 2 != ctx->next_ticket))
+    return fail(ctx, KZG_E_BAD_ARG, "no call in flight under this ticket");
+  DeviceGuard g(ctx->device);
+  KZG_CUDA_OK(ctx, cudaEventSynchronize(q.done));
+  memcpy(out_c48, q.out_host, 48);
+  q.busy = false;
+  update_timers(ctx);
+  return KZG_OK;
 }
 
 int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count, uint8_t out_c48[48]) {

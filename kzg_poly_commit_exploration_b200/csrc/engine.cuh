@@ -56,6 +56,16 @@ struct kzg_ctx {
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
+  // two-deep submission queue of kzg_msm_g1_submit / kzg_msm_g1_wait (host->device copy of call k+1 beside call k)
+  struct Pending {
+    void* scalars = nullptr; size_t cap = 0;   // device staging of this slot
+    void* result = nullptr;                    // device: one G1Xyzz + 48 compressed bytes
+    uint8_t* out_host = nullptr;               // pinned, 48 bytes
+    cudaEvent_t copied = nullptr, done = nullptr;
+    int32_t status = 0;
+    bool busy = false;
+  } pending[2];
+  uint32_t next_ticket = 0;
 };
 
 struct kzg_setup {

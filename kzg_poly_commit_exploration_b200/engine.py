@@ -111,6 +111,18 @@ class Context:
         self.check(N.lib().kzg_msm_g1(self._h, setup._h, _ptr(scalars_le32), n, o))
         return bytes(o)
 
+    def msm_g1_submit(self, setup: "Setup", scalars_le32, n: int | None = None) -> int:
+        """Queue one MSM (at most two in flight); the host buffer must outlive the matching msm_g1_wait."""
+        n = len(scalars_le32) // 32 if n is None else n
+        t = C.c_int32(-1)
+        self.check(N.lib().kzg_msm_g1_submit(self._h, setup._h, _ptr(scalars_le32), n, C.byref(t)))
+        return t.value
+
+    def msm_g1_wait(self, ticket: int) -> bytes:
+        o = N.out(48)
+        self.check(N.lib().kzg_msm_g1_wait(self._h, ticket, o))
+        return bytes(o)
+
     def evaluate(self, coeffs_le32, z_le: bytes, n: int | None = None) -> bytes:
         n = len(coeffs_le32) // 32 if n is None else n
         o = N.out(32)

@@ -435,6 +435,31 @@ def test_sharded_partials_combine(ctx):
         st.close()
 
 
+def test_msm_submit_wait_two_in_flight(ctx, setup8k):
+    """kzg_msm_g1_submit / kzg_msm_g1_wait: same bytes as the one-shot call, whatever the interleaving."""
+    from kzg_poly_commit_exploration_b200._native import KzgNativeError
+    sizes = [3000, 17, 0, 8192, 1, 2999]
+    sets = [util.scalar_stream_bytes(0x51 + i, n) for i, n in enumerate(sizes)]
+    expect = [ctx.msm_g1(setup8k, s, n) for s, n in zip(sets, sizes)]
+    assert expect[2] == O.g1_compress(None)
+    t0 = ctx.msm_g1_submit(setup8k, sets[0], sizes[0])
+    t1 = ctx.msm_g1_submit(setup8k, sets[1], sizes[1])
+    with pytest.raises(KzgNativeError):
+        ctx.msm_g1_submit(setup8k, sets[2], sizes[2])          # two already in flight
+    assert ctx.msm_g1_wait(t0) == expect[0]
+    with pytest.raises(KzgNativeError):
+        ctx.msm_g1_wait(t0)                                     # already collected
+    prev = t1
+    for i in range(2, len(sets)):
+        t = ctx.msm_g1_submit(setup8k, sets[i], sizes[i])
+        assert ctx.msm_g1_wait(prev) == expect[i - 1]
+        prev = t
+    assert ctx.msm_g1(setup8k, sets[0], sizes[0]) == expect[0]   # the one-shot call still works beside a pending ticket
+    assert ctx.msm_g1_wait(prev) == expect[-1]
+    with pytest.raises(KzgNativeError):
+        ctx.msm_g1_submit(setup8k, sets[0], 8193)               # more scalars than bases (src/polynomial.rs:201-205)
+
+
 # ---- BASELINE config C2: degree 2^16 ------------------------------------------------------------------
 def test_config_c2_degree_65536(ctx):
     n = 65537
