@@ -157,9 +157,18 @@ def run_ours(args):
     ext_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     torch.cuda.synchronize()
 
+    use_p2p = world > 1 and args.exchange == "p2p"
+    if use_p2p:
+        from kzg_poly_commit_exploration_b200 import parallel
+        parallel.connect_peers(ctx, world, rank)     # NCCL carries the 64-byte IPC handles, once
+
     def step_dev():
         if world == 1:
             return ctx.msm_g1_dev(setup, scal_dev.data_ptr(), per)
+        if use_p2p:
+            # partial MSM, then ONE kernel that stores the 192-byte partial into every peer's mailbox over NVLink,
+            # waits for the others, folds and compresses (msm_tail.cu k_exchange_combine): no NCCL on the data path
+            return ctx.msm_g1_sharded_dev(setup, scal_dev.data_ptr(), per)
         # partial MSM, NCCL all-gather of the 192-byte partials and the fold are enqueued in order on the
         # engine's stream (torch sees it as an ExternalStream): no host synchronisation until the 48-byte result
         ctx.msm_g1_partial_dev(setup, scal_dev.data_ptr(), per, partial.data_ptr())
@@ -282,7 +291,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"single G1 commit-MSM n=2^{LOG_N} (BASELINE config C3), uniform scalars U(0xC3,i), "
                                    "bench-secret setup", "window_bits": windows["c"], "windows": windows["W"],
-                       "sharding": f"point range, {per} points/GPU", "l2": "inputs larger than L2 (table "
+                       "sharding": f"point range, {per} points/GPU",
+                       "exchange": ("none" if world == 1 else "peer stores over NVLink + fold + compress in one kernel "
+                                    "(k_exchange_combine)" if use_p2p else "NCCL all-gather of 192-byte partials + fold kernel"),
+                       "l2": "inputs larger than L2 (table "
                        f"{windows['W'] * per * 96 / 2**20:.0f} MiB + scalars {per * 32 / 2**20:.0f} MiB per GPU)",
                        "precomputed_table_s": round(table_s, 3)},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": per * 32 * world,
@@ -324,7 +336,11 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": cpu_val, "unit": "points/s", "cores": threads, "kind": "port",
                                     "sample": f"{cpu_points}-point prefix of the same scalars, reference naive loop "
                                               f"(src/polynomial.rs:207-212) split over {threads} threads, {cpu_dt:.2f} s"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # tensors that were used on the engine's stream (through the ExternalStream) must go before the stream does:
+    # torch's pinned-memory allocator records an event on every stream a block was used on when the block is freed
+    del host, scal_dev, partial, gathered
+    torch.cuda.synchronize()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -456,6 +472,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--window", type=int, default=int(os.environ.get("KZG_WINDOW", "0")))
+    ap.add_argument("--exchange", default=os.environ.get("KZG_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
+                    help="multi-GPU exchange of the partial sums: fused peer-memory kernel (default) or NCCL all-gather")
     ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BLOBS", "4096")),
                     help="size of the secondary blob batch (0 = skip)")
     ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "15")))

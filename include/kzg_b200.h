@@ -148,6 +148,18 @@ int32_t kzg_msm_g1_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev
 /* partial sum of a shard, left on the device as a KZG_G1_PARTIAL_BYTES blob (for all-gather) */
 int32_t kzg_msm_g1_partial_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev,
                                uint64_t n, void* partial_dev);
+/* ---- multi-GPU (one process per GPU, BASELINE config C3): the per-GPU partial sums are exchanged by direct stores
+ * into peer memory over NVLink and folded + compressed by the same kernel (no NCCL call on the data path).
+ *   kzg_p2p_init     allocates this rank's mailbox and returns its CUDA IPC handle (KZG_P2P_HANDLE_BYTES bytes);
+ *   kzg_p2p_connect  takes the handles of ALL ranks, rank-major (world x KZG_P2P_HANDLE_BYTES; how they travel
+ *                    between the processes is the caller's business: torch.distributed, MPI, a file ...);
+ *   kzg_msm_g1_sharded_dev  is collective: every rank calls it with its shard, every rank receives the full result.
+ * A rank that never shows up turns into KZG_E_CUDA after ~2 s instead of a hang. */
+#define KZG_P2P_HANDLE_BYTES 64
+int32_t kzg_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_out[KZG_P2P_HANDLE_BYTES]);
+int32_t kzg_p2p_connect(kzg_ctx* ctx, const uint8_t* handles);
+int32_t kzg_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,
+                               uint8_t out_c48[48]);
 /* fold `count` partial sums (device) into one compressed point */
 int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count,
                            uint8_t out_c48[48]);

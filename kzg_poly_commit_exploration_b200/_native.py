@@ -56,6 +56,9 @@ SIGNATURES = {
     "kzg_msm_g1_wait": (_i32, [_vp, _i32, _vp]),
     "kzg_msm_g1_partial_dev": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "kzg_g1_combine_dev": (_i32, [_vp, _vp, _u64, _vp]),
+    "kzg_p2p_init": (_i32, [_vp, _i32, _i32, _vp]),
+    "kzg_p2p_connect": (_i32, [_vp, _vp]),
+    "kzg_msm_g1_sharded_dev": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "kzg_commit_batch_dev": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp]),
     "kzg_open_batch_dev": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "kzg_evaluate_dev": (_i32, [_vp, _vp, _u64, _vp, _vp]),

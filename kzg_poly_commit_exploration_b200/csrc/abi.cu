@@ -138,6 +138,12 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
     if (q.copied) cudaEventDestroy(q.copied);
     if (q.done) cudaEventDestroy(q.done);
   }
+  for (int r = 0; r < ctx->p2p_world; r++) {
+    if (!ctx->p2p_box[r]) continue;
+    if (r == ctx->p2p_rank) cudaFree(ctx->p2p_box[r]); else cudaIpcCloseMemHandle(ctx->p2p_box[r]);
+  }
+  if (ctx->p2p_out) cudaFree(ctx->p2p_out);
+  if (ctx->p2p_out_host) cudaFreeHost(ctx->p2p_out_host);
   if (ctx->gtable) cudaFree(ctx->gtable);
   if (ctx->g2table) cudaFree(ctx->g2table);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -189,6 +195,7 @@ int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "acc_min_entries") ctx->opt_acc_min_entries = (int)std::max<int64_t>(1, value);
   else if (n == "coop_tail") ctx->opt_coop_tail = (int)value;
   else if (n == "tree_k") ctx->opt_tree_k = (int)value;
+  else if (n == "p2p_timeout_ms") ctx->p2p_timeout_cycles = std::max<int64_t>(1, value) * 2000000ll;   // ~2 GHz
   else if (n == "acc_minblocks") ctx->opt_acc_minblocks = (int)value;
   else if (n == "inv_top_fan") ctx->opt_inv_top_fan = (int)value;
   else if (n == "inv_top") ctx->opt_inv_top = std::max<int64_t>(8, value);
@@ -412,6 +419,59 @@ int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
   memcpy(out_c48, q.out_host, 48);
   q.busy = false;
   update_timers(ctx);
+  return KZG_OK;
+}
+
+// ---- multi-GPU exchange over peer memory ---------------------------------------------------------------------------
+int32_t kzg_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_out[KZG_P2P_HANDLE_BYTES]) {
+  if (!ctx || !handle_out || world < 1 || world > KZG_MAX_PEERS || rank < 0 || rank >= world) return KZG_E_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == KZG_P2P_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard g(ctx->device);
+  if (ctx->p2p_box[ctx->p2p_rank] && ctx->p2p_world) return fail(ctx, KZG_E_BAD_ARG, "peer exchange already initialised on this context");
+  void* box = nullptr;
+  KZG_CUDA_OK(ctx, cudaMalloc(&box, sizeof(PeerMailbox)));
+  KZG_CUDA_OK(ctx, cudaMemset(box, 0, sizeof(PeerMailbox)));
+  KZG_CUDA_OK(ctx, cudaMalloc(&ctx->p2p_out, 64));
+  KZG_CUDA_OK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->p2p_out_host), 64, cudaHostAllocDefault));
+  KZG_CUDA_OK(ctx, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  KZG_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, box));
+  memcpy(handle_out, &h, sizeof(h));
+  ctx->p2p_world = world; ctx->p2p_rank = rank; ctx->p2p_box[rank] = box; ctx->p2p_seq = 0; ctx->p2p_connected = false;
+  return KZG_OK;
+}
+
+int32_t kzg_p2p_connect(kzg_ctx* ctx, const uint8_t* handles) {
+  if (!ctx || !handles || ctx->p2p_world < 1 || !ctx->p2p_box[ctx->p2p_rank]) return KZG_E_BAD_ARG;
+  DeviceGuard g(ctx->device);
+  for (int r = 0; r < ctx->p2p_world; r++) {
+    if (r == ctx->p2p_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * KZG_P2P_HANDLE_BYTES, sizeof(h));
+    KZG_CUDA_OK(ctx, cudaIpcOpenMemHandle(&ctx->p2p_box[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  ctx->p2p_connected = true;
+  return KZG_OK;
+}
+
+int32_t kzg_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]) {
+  if (!ctx || !s || !out_c48) return KZG_E_BAD_ARG;
+  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  if (!ctx->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
+  DeviceGuard g(ctx->device);
+  void* r;
+  KZG_TRY(scratch_get(ctx, SCR_MISC, 1024, &r));
+  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
+  KZG_TRY(msm_any(ctx, s, reinterpret_cast<const uint8_t*>(scalars_dev), n, res));
+  uint8_t* od = reinterpret_cast<uint8_t*>(ctx->p2p_out);
+  KZG_TRY(exchange_combine(ctx, res, od, reinterpret_cast<uint32_t*>(od + 48)));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(ctx->p2p_out_host, od, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  update_timers(ctx);
+  uint32_t st;
+  memcpy(&st, ctx->p2p_out_host + 48, 4);
+  if (st != 0) return fail(ctx, KZG_E_CUDA, "peer exchange timed out: a rank did not publish its partial sum");
+  memcpy(out_c48, ctx->p2p_out_host, 48);
   return KZG_OK;
 }
 

@@ -20,6 +20,7 @@ enum ScratchSlot {
   SCR_COUNT
 };
 
+constexpr int KZG_MAX_PEERS = 32;
 }  // namespace kzg
 
 struct kzg_ctx {
@@ -66,6 +67,14 @@ struct kzg_ctx {
     bool busy = false;
   } pending[2];
   uint32_t next_ticket = 0;
+  // multi-GPU exchange over peer memory (msm_tail.cu k_exchange_combine): box[r] = rank r's mailbox as seen from here
+  int p2p_world = 0, p2p_rank = 0;
+  bool p2p_connected = false;
+  void* p2p_box[kzg::KZG_MAX_PEERS] = {};
+  uint32_t p2p_seq = 0;
+  long long p2p_timeout_cycles = 1ll << 32;      // ~2 s of spinning before a missing peer becomes an error
+  void* p2p_out = nullptr;                       // device: 48 result bytes + status word
+  uint8_t* p2p_out_host = nullptr;               // pinned mirror
 };
 
 struct kzg_setup {
@@ -152,6 +161,14 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
 int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev);
 // XYZZ (device) x count -> 48-byte compressed (device)
 int32_t finalize_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, uint8_t* out_c48_dev);
+
+// one partial sum per GPU -> every GPU's mailbox (peer stores), fold, compress: out_c48_dev[48], *status_dev = 0 / 1 (timeout)
+struct PeerMailbox {
+  G1Xyzz slot[2][KZG_MAX_PEERS];     // [parity of the call][source rank]
+  uint32_t flag[2][KZG_MAX_PEERS];   // sequence number of the partial in the slot
+};
+struct PeerTable { PeerMailbox* box[KZG_MAX_PEERS]; };
+int32_t exchange_combine(kzg_ctx* ctx, const G1Xyzz* mine_dev, uint8_t* out_c48_dev, uint32_t* status_dev);
 
 // ---- batch.cu (K5) ---------------------------------------------------------------------------
 // blobs MSMs of n scalars each against the fixed-base table; out: blobs XYZZ

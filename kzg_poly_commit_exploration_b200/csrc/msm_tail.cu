@@ -379,6 +379,77 @@ k_sum_coop(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ o
   if (threadIdx.x == 0) out[blockIdx.x] = X;
 }
 
+// ---- multi-GPU: exchange + fold + compress in ONE kernel over NVLink peer memory ---------------------------------
+// Point-range sharding leaves one 192-byte XYZZ partial sum per GPU.  Instead of an NCCL all-gather followed by a
+// fold kernel and a compression kernel, every rank runs this single block: lane r of warp 0 STORES the rank's partial
+// straight into rank r's mailbox (peer memory mapped through CUDA IPC, NVLink 5 / NVSwitch), publishes it with a
+// release store of the call's sequence number, then spins (acquire loads) on its own mailbox until all `world`
+// partials of this call have landed; the four warps fold them with cooperative additions and thread 0 converts to
+// affine and compresses.  Mailbox slots are double-buffered by the parity of the sequence number: a rank can only
+// be one call ahead of a peer (its next publish needs the peer's current one), so parity p is never overwritten while
+// a peer still reads it.  A bounded spin turns a dead peer into an error instead of a hang.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(128)
+k_exchange_combine(const G1Xyzz* __restrict__ mine, PeerTable peers, int world, int rank, uint32_t seq,
+                   long long timeout_cycles, uint8_t* __restrict__ out_c48, uint32_t* __restrict__ status) {
+  __shared__ CoopBuf sh;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t par = seq & 1u;
+  PeerMailbox* my = peers.box[rank];
+  int ok = 1;
+  if (w == 0 && lane < (uint32_t)world) {
+    const uint4* src = reinterpret_cast<const uint4*>(mine);
+    PeerMailbox* mb = peers.box[lane];
+    volatile uint4* dst = reinterpret_cast<volatile uint4*>(&mb->slot[par][rank]);
+#pragma unroll
+    for (int i = 0; i < 12; i++) { uint4 v = src[i]; dst[i].x = v.x; dst[i].y = v.y; dst[i].z = v.z; dst[i].w = v.w; }
+    __threadfence_system();
+    st_release_sys(&mb->flag[par][rank], seq);
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(&my->flag[par][lane]) - seq) < 0) {
+      if (clock64() - t0 > timeout_cycles) { ok = 0; break; }
+      __nanosleep(64);
+    }
+  }
+  if (!__syncthreads_and(ok)) {
+    if (threadIdx.x == 0) *status = 1u;
+    return;
+  }
+  G1Xyzz X;
+  if (lane < (uint32_t)world) {
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(&my->slot[par][lane]);
+#pragma unroll
+    for (int i = 0; i < 12; i++) { X.x.v[i] = q[i]; X.y.v[i] = q[12 + i]; X.zz.v[i] = q[24 + i]; X.zzz.v[i] = q[36 + i]; }
+  } else set_inf(X);
+  coop_tree_sum(X, &sh, w, lane);
+  if (threadIdx.x == 0) {
+    G1Affine a; to_affine(a, X);
+    uint8_t buf[48];
+    compress(buf, a);
+    for (int k = 0; k < 48; k++) out_c48[k] = buf[k];
+    *status = 0u;
+  }
+}
+
+int32_t exchange_combine(kzg_ctx* ctx, const G1Xyzz* mine_dev, uint8_t* out_c48_dev, uint32_t* status_dev) {
+  if (ctx->p2p_world < 1 || !ctx->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
+  PeerTable t;
+  for (int r = 0; r < KZG_MAX_PEERS; r++) t.box[r] = r < ctx->p2p_world ? reinterpret_cast<PeerMailbox*>(ctx->p2p_box[r]) : nullptr;
+  const uint32_t seq = ++ctx->p2p_seq;
+  k_exchange_combine<<<1, 128, 0, ctx->stream>>>(mine_dev, t, ctx->p2p_world, ctx->p2p_rank, seq, ctx->p2p_timeout_cycles,
+                                                 out_c48_dev, status_dev);
+  KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
 int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev) {
   if (count == 0) {
     k_set_inf_tail<<<1, 32, 0, ctx->stream>>>(out_dev, 1);

@@ -162,6 +162,21 @@ class Context:
     def msm_g1_partial_dev(self, setup: "Setup", scalars_dev: int, n: int, partial_dev: int):
         self.check(N.lib().kzg_msm_g1_partial_dev(self._h, setup._h, _ptr(scalars_dev), n, _ptr(partial_dev)))
 
+    def p2p_init(self, world: int, rank: int) -> bytes:
+        """allocate this rank's peer mailbox; returns its CUDA IPC handle (see parallel.connect_peers)"""
+        h = N.out(64)
+        self.check(N.lib().kzg_p2p_init(self._h, world, rank, h))
+        return bytes(h)
+
+    def p2p_connect(self, handles: bytes):
+        self.check(N.lib().kzg_p2p_connect(self._h, _ptr(handles)))
+
+    def msm_g1_sharded_dev(self, setup: "Setup", scalars_dev: int, n: int) -> bytes:
+        """collective: partial MSM of this rank's shard, exchange over peer memory, fold + compress in one kernel"""
+        o = N.out(48)
+        self.check(N.lib().kzg_msm_g1_sharded_dev(self._h, setup._h, _ptr(scalars_dev), n, o))
+        return bytes(o)
+
     def g1_combine_dev(self, partials_dev: int, count: int) -> bytes:
         o = N.out(48)
         self.check(N.lib().kzg_g1_combine_dev(self._h, _ptr(partials_dev), count, o))

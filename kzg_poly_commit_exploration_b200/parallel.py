@@ -24,3 +24,26 @@ def gather_blobs(blob, world: int):
     out = torch.empty(blob.numel() * world, dtype=blob.dtype, device=blob.device)
     dist.all_gather_into_tensor(out, blob.contiguous())
     return out
+
+
+def exchange_handles(handle: bytes, world: int) -> bytes:
+    """all-gather one fixed-size opaque handle per rank (host objects), rank-major"""
+    import torch.distributed as dist
+
+    if world == 1:
+        return handle
+    got = [None] * world
+    dist.all_gather_object(got, handle)
+    assert all(isinstance(h, bytes) and len(h) == len(handle) for h in got)
+    return b"".join(got)
+
+
+def connect_peers(ctx, world: int, rank: int) -> None:
+    """Map every rank's mailbox into this process (CUDA IPC over NVLink) so that kzg_msm_g1_sharded_dev can exchange
+    the per-GPU partial sums with plain peer stores: torch.distributed only carries the 64-byte handles, once."""
+    import torch.distributed as dist
+
+    handles = exchange_handles(ctx.p2p_init(world, rank), world)
+    ctx.p2p_connect(handles)
+    if world > 1:
+        dist.barrier()

@@ -460,6 +460,48 @@ def test_msm_submit_wait_two_in_flight(ctx, setup8k):
         ctx.msm_g1_submit(setup8k, sets[0], 8193)               # more scalars than bases (src/polynomial.rs:201-205)
 
 
+def test_peer_exchange_single_rank_and_dead_peer():
+    """k_exchange_combine (peer-memory exchange + fold + compress in one kernel): world = 1 degenerates to
+    publish-to-self; a rank that never publishes becomes an error after the bounded spin, not a hang."""
+    import torch
+    import kzg_poly_commit_exploration_b200 as pkg
+    from kzg_poly_commit_exploration_b200._native import KzgNativeError
+    n = 5000
+    scal = util.scalar_stream_bytes(0xC3, n)
+    dev = torch.device("cuda:0")
+    sc = torch.frombuffer(bytearray(scal), dtype=torch.uint8).to(dev)
+    c1 = pkg.Context(0)
+    st = c1.setup_generate(SECRET, n)
+    with pytest.raises(KzgNativeError):
+        c1.msm_g1_sharded_dev(st, sc.data_ptr(), n)            # not connected yet
+    h = c1.p2p_init(1, 0)
+    assert len(h) == 64
+    c1.p2p_connect(h)
+    expect = O.g1_compress(O.commit_known_secret(util.to_ints(scal), S))
+    for _ in range(3):                                          # both mailbox parities
+        assert c1.msm_g1_sharded_dev(st, sc.data_ptr(), n) == expect
+    st.close(); c1.close()
+    # "rank 0 of 2" whose peer (a second process on the same GPU) maps its mailbox but never publishes
+    import os, subprocess, sys
+    ghost_src = ("import sys; sys.path.insert(0, %r); import kzg_poly_commit_exploration_b200 as pkg; c = pkg.Context(0); "
+                 "print(c.p2p_init(2, 1).hex(), flush=True); sys.stdin.readline(); c.close()" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    ghost = subprocess.Popen([sys.executable, "-c", ghost_src], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+    try:
+        h1 = bytes.fromhex(ghost.stdout.readline().strip())
+        assert len(h1) == 64
+        c2 = pkg.Context(0)
+        st = c2.setup_generate(SECRET, n)
+        h0 = c2.p2p_init(2, 0)
+        c2.p2p_connect(h0 + h1)
+        c2.set_option("p2p_timeout_ms", 50)
+        with pytest.raises(KzgNativeError, match="timed out"):
+            c2.msm_g1_sharded_dev(st, sc.data_ptr(), n)
+        st.close(); c2.close()
+    finally:
+        ghost.stdin.write("\n"); ghost.stdin.flush()
+        ghost.wait(timeout=60)
+
+
 # ---- BASELINE config C2: degree 2^16 ------------------------------------------------------------------
 def test_config_c2_degree_65536(ctx):
     n = 65537

@@ -81,3 +81,30 @@ def test_two_rank_gather_and_fold_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+def _handle_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    from kzg_poly_commit_exploration_b200 import parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    handle = bytes([rank + 1]) * 64                      # stands for the CUDA IPC handle of rank `rank`'s mailbox
+    ret.put((rank, parallel.exchange_handles(handle, world)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_handle_exchange_gloo():
+    """host side of parallel.connect_peers: every rank ends up with all mailbox handles, rank-major"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_handle_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(ret.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert got[0] == got[1] == bytes([1]) * 64 + bytes([2]) * 64
