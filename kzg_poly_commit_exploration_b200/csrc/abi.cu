@@ -142,8 +142,7 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
     if (!ctx->p2p_box[r]) continue;
     if (r == ctx->p2p_rank) cudaFree(ctx->p2p_box[r]); else cudaIpcCloseMemHandle(ctx->p2p_box[r]);
   }
-  if (ctx->p2p_out) cudaFree(ctx->p2p_out);
-  if (ctx->p2p_out_host) cudaFreeHost(ctx->p2p_out_host);
+  if (ctx->lane1) kzg_ctx_destroy(ctx->lane1);
   if (ctx->gtable) cudaFree(ctx->gtable);
   if (ctx->g2table) cudaFree(ctx->g2table);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -160,6 +159,7 @@ const char* kzg_last_error(const kzg_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int32_t kzg_ctx_sync(kzg_ctx* ctx) {
   DeviceGuard g(ctx->device);
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->lane1) KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->lane1->stream));
   update_timers(ctx);
   return KZG_OK;
 }
@@ -172,13 +172,17 @@ int32_t kzg_ctx_timer_start(kzg_ctx* ctx) {
 
 int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
   DeviceGuard g(ctx->device);
+  if (ctx->lane1) {     // the interval ends when BOTH lanes are done
+    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->lane1->ev_t[1], ctx->lane1->stream));
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane1->ev_t[1], 0));
+  }
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_t[1], ctx->stream));
   KZG_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_t[1]));
   KZG_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev_t[0], ctx->ev_t[1]));
   return KZG_OK;
 }
 
-uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) { return ctx->launches; }
+uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) { return ctx->launches + (ctx->lane1 ? ctx->lane1->launches : 0); }
 
 void* kzg_ctx_stream(const kzg_ctx* ctx) { return ctx ? reinterpret_cast<void*>(ctx->stream) : nullptr; }
 
@@ -373,39 +377,91 @@ int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32
   return kzg_msm_g1_dev(ctx, s, d, n, out_c48);
 }
 
-int32_t kzg_msm_g1_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket) {
-  if (!ctx || !s || (!scalars_le32 && n) || !ticket) return KZG_E_BAD_ARG;
+// ---- two calls in flight -------------------------------------------------------------------------------------------
+// Even tickets run on the context itself, odd tickets on a hidden sibling context of the same device (own streams, own
+// scratch): the host->device copy AND the front of call k+1 overlap the latency-bound tail of call k (bucket
+// reduction: a few hundred warps for ~0.6 ms), which is worth 13 % at n = 2^20 and 30 % at n = 2^17.
+static void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
+  dst->opt_msm_window = src->opt_msm_window; dst->opt_fixed_window = src->opt_fixed_window;
+  dst->opt_reduce_chunk = src->opt_reduce_chunk; dst->opt_heavy_cap = src->opt_heavy_cap; dst->opt_acc_split = src->opt_acc_split;
+  dst->opt_tree_min_rows = src->opt_tree_min_rows; dst->opt_tree_chunk_rows = src->opt_tree_chunk_rows;
+  dst->opt_tree_min_pairs = src->opt_tree_min_pairs; dst->opt_inv_top_fan = src->opt_inv_top_fan; dst->opt_inv_top = src->opt_inv_top;
+  dst->opt_msm_tree_rounds = src->opt_msm_tree_rounds; dst->opt_acc_min_entries = src->opt_acc_min_entries;
+  dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_acc_minblocks = src->opt_acc_minblocks;
+}
+
+static int32_t lane_of(kzg_ctx* ctx, uint32_t ticket, kzg_ctx** lane) {
+  *lane = ctx;
+  if (!(ticket & 1)) return KZG_OK;
+  if (!ctx->lane1) {
+    int32_t st = kzg_ctx_create(&ctx->lane1, ctx->device);
+    if (st != KZG_OK) return fail(ctx, st, "could not create the second lane of the submission queue");
+  }
+  copy_options(ctx->lane1, ctx);
+  *lane = ctx->lane1;
+  return KZG_OK;
+}
+
+// host == true: `scalars` is a host buffer, copied on the lane's copy stream; sharded == true: the result is the
+// fold of every rank's partial (peer exchange), else this context's own sum
+static int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host, bool sharded,
+                             int32_t* ticket) {
+  if (!ctx || !s || (!scalars && n) || !ticket) return KZG_E_BAD_ARG;
   if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  if (sharded && !ctx->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
   DeviceGuard g(ctx->device);
   const uint32_t t = ctx->next_ticket;
   kzg_ctx::Pending& q = ctx->pending[t & 1];
   if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "two calls are already in flight: wait for the older ticket first");
+  kzg_ctx* lane;
+  KZG_TRY(lane_of(ctx, t, &lane));
+  if (!s->msm_tab && !(s->fix_tab && n <= s->fix_n)) {      // built once, on the main lane, before any lane reads it
+    KZG_TRY(ensure_msm_table(ctx, s));
+    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if (!q.copied) {
     KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.copied, cudaEventDisableTiming));
     KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
     KZG_CUDA_OK(ctx, cudaMalloc(&q.result, 512));
     KZG_CUDA_OK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&q.out_host), 64, cudaHostAllocDefault));
   }
-  const size_t bytes = n ? n * 32 : 32;
-  if (q.cap < bytes) {
-    if (q.scalars) { KZG_CUDA_OK(ctx, cudaFree(q.scalars)); q.scalars = nullptr; q.cap = 0; }
-    KZG_CUDA_OK(ctx, cudaMalloc(&q.scalars, bytes));
-    q.cap = bytes;
+  const uint8_t* dev_scalars = reinterpret_cast<const uint8_t*>(scalars);
+  if (host) {
+    const size_t bytes = n ? n * 32 : 32;
+    if (q.cap < bytes) {
+      if (q.scalars) { KZG_CUDA_OK(ctx, cudaFree(q.scalars)); q.scalars = nullptr; q.cap = 0; }
+      KZG_CUDA_OK(ctx, cudaMalloc(&q.scalars, bytes));
+      q.cap = bytes;
+    }
+    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.scalars, scalars, n * 32, cudaMemcpyHostToDevice, lane->copy_stream));
+    KZG_CUDA_OK(ctx, cudaEventRecord(q.copied, lane->copy_stream));
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(lane->stream, q.copied, 0));
+    dev_scalars = reinterpret_cast<const uint8_t*>(q.scalars);
   }
-  // the copy runs on the copy stream, beside whatever the engine stream is still computing
-  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.scalars, scalars_le32, n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-  KZG_CUDA_OK(ctx, cudaEventRecord(q.copied, ctx->copy_stream));
-  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, q.copied, 0));
   G1Xyzz* res = reinterpret_cast<G1Xyzz*>(q.result);
   uint8_t* out_dev = reinterpret_cast<uint8_t*>(q.result) + 256;
-  KZG_TRY(msm_any(ctx, s, reinterpret_cast<const uint8_t*>(q.scalars), n, res));
-  KZG_TRY(finalize_points(ctx, res, 1, out_dev));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.out_host, out_dev, 48, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaEventRecord(q.done, ctx->stream));
-  q.busy = true;
+  int32_t st = msm_any(lane, s, dev_scalars, n, res);
+  if (st == KZG_OK) {
+    if (sharded) st = exchange_combine(lane, ctx, t + 1, res, out_dev, reinterpret_cast<uint32_t*>(out_dev + 48));
+    else st = finalize_points(lane, res, 1, out_dev);
+  }
+  if (st != KZG_OK) { if (lane != ctx) ctx->err = lane->err; return st; }
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.out_host, out_dev, 64, cudaMemcpyDeviceToHost, lane->stream));
+  KZG_CUDA_OK(ctx, cudaEventRecord(q.done, lane->stream));
+  q.busy = true; q.sharded = sharded;
   *ticket = (int32_t)t;
   ctx->next_ticket = t + 1;
   return KZG_OK;
+}
+
+int32_t kzg_msm_g1_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket) {
+  return submit_common(ctx, s, scalars_le32, n, true, false, ticket);
+}
+int32_t kzg_msm_g1_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket) {
+  return submit_common(ctx, s, scalars_dev, n, false, false, ticket);
+}
+int32_t kzg_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket) {
+  return submit_common(ctx, s, scalars_dev, n, false, true, ticket);
 }
 
 int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
@@ -416,9 +472,13 @@ int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
     return fail(ctx, KZG_E_BAD_ARG, "no call in flight under this ticket");
   DeviceGuard g(ctx->device);
   KZG_CUDA_OK(ctx, cudaEventSynchronize(q.done));
-  memcpy(out_c48, q.out_host, 48);
   q.busy = false;
-  update_timers(ctx);
+  if (q.sharded) {
+    uint32_t st;
+    memcpy(&st, q.out_host + 48, 4);
+    if (st != 0) return fail(ctx, KZG_E_CUDA, "peer exchange timed out: a rank did not publish its partial sum");
+  }
+  memcpy(out_c48, q.out_host, 48);
   return KZG_OK;
 }
 
@@ -431,13 +491,11 @@ int32_t kzg_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_o
   void* box = nullptr;
   KZG_CUDA_OK(ctx, cudaMalloc(&box, sizeof(PeerMailbox)));
   KZG_CUDA_OK(ctx, cudaMemset(box, 0, sizeof(PeerMailbox)));
-  KZG_CUDA_OK(ctx, cudaMalloc(&ctx->p2p_out, 64));
-  KZG_CUDA_OK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->p2p_out_host), 64, cudaHostAllocDefault));
   KZG_CUDA_OK(ctx, cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   KZG_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, box));
   memcpy(handle_out, &h, sizeof(h));
-  ctx->p2p_world = world; ctx->p2p_rank = rank; ctx->p2p_box[rank] = box; ctx->p2p_seq = 0; ctx->p2p_connected = false;
+  ctx->p2p_world = world; ctx->p2p_rank = rank; ctx->p2p_box[rank] = box; ctx->p2p_connected = false;
   return KZG_OK;
 }
 
@@ -456,23 +514,9 @@ int32_t kzg_p2p_connect(kzg_ctx* ctx, const uint8_t* handles) {
 
 int32_t kzg_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]) {
   if (!ctx || !s || !out_c48) return KZG_E_BAD_ARG;
-  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  if (!ctx->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
-  DeviceGuard g(ctx->device);
-  void* r;
-  KZG_TRY(scratch_get(ctx, SCR_MISC, 1024, &r));
-  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
-  KZG_TRY(msm_any(ctx, s, reinterpret_cast<const uint8_t*>(scalars_dev), n, res));
-  uint8_t* od = reinterpret_cast<uint8_t*>(ctx->p2p_out);
-  KZG_TRY(exchange_combine(ctx, res, od, reinterpret_cast<uint32_t*>(od + 48)));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(ctx->p2p_out_host, od, 64, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  update_timers(ctx);
-  uint32_t st;
-  memcpy(&st, ctx->p2p_out_host + 48, 4);
-  if (st != 0) return fail(ctx, KZG_E_CUDA, "peer exchange timed out: a rank did not publish its partial sum");
-  memcpy(out_c48, ctx->p2p_out_host, 48);
-  return KZG_OK;
+  int32_t t = -1;
+  KZG_TRY(kzg_msm_g1_sharded_submit_dev(ctx, s, scalars_dev, n, &t));
+  return kzg_msm_g1_wait(ctx, t, out_c48);
 }
 
 int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count, uint8_t out_c48[48]) {

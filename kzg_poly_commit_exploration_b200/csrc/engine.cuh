@@ -21,6 +21,8 @@ enum ScratchSlot {
 };
 
 constexpr int KZG_MAX_PEERS = 32;
+constexpr int KZG_P2P_DEPTH = 4;      // mailbox slots per peer: with at most two calls in flight per rank, call k + 2 may
+                                     // overwrite the slot of call k - 2, which every rank has finished reading (msm_tail.cu)
 }  // namespace kzg
 
 struct kzg_ctx {
@@ -60,21 +62,21 @@ struct kzg_ctx {
   // two-deep submission queue of kzg_msm_g1_submit / kzg_msm_g1_wait (host->device copy of call k+1 beside call k)
   struct Pending {
     void* scalars = nullptr; size_t cap = 0;   // device staging of this slot
-    void* result = nullptr;                    // device: one G1Xyzz + 48 compressed bytes
-    uint8_t* out_host = nullptr;               // pinned, 48 bytes
+    void* result = nullptr;                    // device: one G1Xyzz + 48 compressed bytes + status word
+    uint8_t* out_host = nullptr;               // pinned, 64 bytes (result + status of a sharded call)
+    bool sharded = false;
     cudaEvent_t copied = nullptr, done = nullptr;
     int32_t status = 0;
     bool busy = false;
   } pending[2];
   uint32_t next_ticket = 0;
+  kzg_ctx* lane1 = nullptr;            // odd tickets run on a hidden sibling context (own streams and scratch) so that the
+                                       // latency-bound tail of one call overlaps the bulk kernels of the next
   // multi-GPU exchange over peer memory (msm_tail.cu k_exchange_combine): box[r] = rank r's mailbox as seen from here
   int p2p_world = 0, p2p_rank = 0;
   bool p2p_connected = false;
   void* p2p_box[kzg::KZG_MAX_PEERS] = {};
-  uint32_t p2p_seq = 0;
   long long p2p_timeout_cycles = 1ll << 32;      // ~2 s of spinning before a missing peer becomes an error
-  void* p2p_out = nullptr;                       // device: 48 result bytes + status word
-  uint8_t* p2p_out_host = nullptr;               // pinned mirror
 };
 
 struct kzg_setup {
@@ -164,11 +166,13 @@ int32_t finalize_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, uint
 
 // one partial sum per GPU -> every GPU's mailbox (peer stores), fold, compress: out_c48_dev[48], *status_dev = 0 / 1 (timeout)
 struct PeerMailbox {
-  G1Xyzz slot[2][KZG_MAX_PEERS];     // [parity of the call][source rank]
-  uint32_t flag[2][KZG_MAX_PEERS];   // sequence number of the partial in the slot
+  G1Xyzz slot[KZG_P2P_DEPTH][KZG_MAX_PEERS];     // [call number mod depth][source rank]
+  uint32_t flag[KZG_P2P_DEPTH][KZG_MAX_PEERS];   // sequence number of the partial in the slot
 };
 struct PeerTable { PeerMailbox* box[KZG_MAX_PEERS]; };
-int32_t exchange_combine(kzg_ctx* ctx, const G1Xyzz* mine_dev, uint8_t* out_c48_dev, uint32_t* status_dev);
+// `ctx` supplies the stream, `owner` the mailboxes; seq = number of this collective call (same on every rank)
+int32_t exchange_combine(kzg_ctx* ctx, const kzg_ctx* owner, uint32_t seq, const G1Xyzz* mine_dev, uint8_t* out_c48_dev,
+                         uint32_t* status_dev);
 
 // ---- batch.cu (K5) ---------------------------------------------------------------------------
 // blobs MSMs of n scalars each against the fixed-base table; out: blobs XYZZ

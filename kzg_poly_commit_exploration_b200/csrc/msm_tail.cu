@@ -385,9 +385,10 @@ k_sum_coop(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ o
 // straight into rank r's mailbox (peer memory mapped through CUDA IPC, NVLink 5 / NVSwitch), publishes it with a
 // release store of the call's sequence number, then spins (acquire loads) on its own mailbox until all `world`
 // partials of this call have landed; the four warps fold them with cooperative additions and thread 0 converts to
-// affine and compresses.  Mailbox slots are double-buffered by the parity of the sequence number: a rank can only
-// be one call ahead of a peer (its next publish needs the peer's current one), so parity p is never overwritten while
-// a peer still reads it.  A bounded spin turns a dead peer into an error instead of a hang.
+// affine and compresses.  Mailbox slots are KZG_P2P_DEPTH = 4 deep, indexed by the call number: a rank has at most
+// two calls in flight (submit k + 2 only after waiting for k), k completes on a rank only when EVERY rank has published
+// k, and a rank publishes k only after it finished k - 2; so when call k + 2 overwrites the slot of call k - 2 every
+// rank is done reading it.  A bounded spin turns a dead peer into an error instead of a hang.
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -402,7 +403,7 @@ k_exchange_combine(const G1Xyzz* __restrict__ mine, PeerTable peers, int world, 
                    long long timeout_cycles, uint8_t* __restrict__ out_c48, uint32_t* __restrict__ status) {
   __shared__ CoopBuf sh;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t par = seq & 1u;
+  const uint32_t par = seq & (KZG_P2P_DEPTH - 1);
   PeerMailbox* my = peers.box[rank];
   int ok = 1;
   if (w == 0 && lane < (uint32_t)world) {
@@ -439,12 +440,12 @@ k_exchange_combine(const G1Xyzz* __restrict__ mine, PeerTable peers, int world, 
   }
 }
 
-int32_t exchange_combine(kzg_ctx* ctx, const G1Xyzz* mine_dev, uint8_t* out_c48_dev, uint32_t* status_dev) {
-  if (ctx->p2p_world < 1 || !ctx->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
+int32_t exchange_combine(kzg_ctx* ctx, const kzg_ctx* owner, uint32_t seq, const G1Xyzz* mine_dev, uint8_t* out_c48_dev,
+                         uint32_t* status_dev) {
+  if (owner->p2p_world < 1 || !owner->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
   PeerTable t;
-  for (int r = 0; r < KZG_MAX_PEERS; r++) t.box[r] = r < ctx->p2p_world ? reinterpret_cast<PeerMailbox*>(ctx->p2p_box[r]) : nullptr;
-  const uint32_t seq = ++ctx->p2p_seq;
-  k_exchange_combine<<<1, 128, 0, ctx->stream>>>(mine_dev, t, ctx->p2p_world, ctx->p2p_rank, seq, ctx->p2p_timeout_cycles,
+  for (int r = 0; r < KZG_MAX_PEERS; r++) t.box[r] = r < owner->p2p_world ? reinterpret_cast<PeerMailbox*>(owner->p2p_box[r]) : nullptr;
+  k_exchange_combine<<<1, 128, 0, ctx->stream>>>(mine_dev, t, owner->p2p_world, owner->p2p_rank, seq, owner->p2p_timeout_cycles,
                                                  out_c48_dev, status_dev);
   KZG_LAUNCHED(ctx);
   return KZG_OK;

@@ -118,6 +118,17 @@ class Context:
         self.check(N.lib().kzg_msm_g1_submit(self._h, setup._h, _ptr(scalars_le32), n, C.byref(t)))
         return t.value
 
+    def msm_g1_submit_dev(self, setup: "Setup", scalars_dev: int, n: int) -> int:
+        t = C.c_int32(-1)
+        self.check(N.lib().kzg_msm_g1_submit_dev(self._h, setup._h, _ptr(scalars_dev), n, C.byref(t)))
+        return t.value
+
+    def msm_g1_sharded_submit_dev(self, setup: "Setup", scalars_dev: int, n: int) -> int:
+        """collective (every rank, same order): partial MSM + peer exchange + fold, collected with msm_g1_wait"""
+        t = C.c_int32(-1)
+        self.check(N.lib().kzg_msm_g1_sharded_submit_dev(self._h, setup._h, _ptr(scalars_dev), n, C.byref(t)))
+        return t.value
+
     def msm_g1_wait(self, ticket: int) -> bytes:
         o = N.out(48)
         self.check(N.lib().kzg_msm_g1_wait(self._h, ticket, o))

@@ -35,7 +35,15 @@ def _worker(rank, world, port, n_total, ret):
     first, count = parallel.shard_range(n_total, world, rank)
     setup = ctx.setup_generate(synthetic.BENCH_SECRET_BE, count, first=first)
     scal = torch.from_numpy(synthetic.scalar_stream(0xC3, count, start=first)).to(torch.device(f"cuda:{rank}"))
-    outs = [ctx.msm_g1_sharded_dev(setup, scal.data_ptr(), count) for _ in range(5)]   # both parities, back to back
+    outs = [ctx.msm_g1_sharded_dev(setup, scal.data_ptr(), count) for _ in range(5)]   # every mailbox slot, back to back
+    # two collective calls in flight on the two lanes of the context
+    prev = None
+    for _ in range(6):
+        t = ctx.msm_g1_sharded_submit_dev(setup, scal.data_ptr(), count)
+        if prev is not None:
+            outs.append(ctx.msm_g1_wait(prev))
+        prev = t
+    outs.append(ctx.msm_g1_wait(prev))
     ret.put((rank, [o.hex() for o in outs]))
     dist.barrier()
     setup.close(); ctx.close()
@@ -67,4 +75,4 @@ def test_two_gpu_peer_exchange_matches_single_gpu():
     ints = [int.from_bytes(full[i].tobytes(), "little") for i in range(n_total)]
     expect = O.g1_compress(O.commit_known_secret(ints, O.fr_from_be_bytes(synthetic.BENCH_SECRET_BE))).hex()
     for r in range(world):
-        assert got[r] == [expect] * 5, r
+        assert got[r] == [expect] * 11, r

@@ -458,6 +458,15 @@ def test_msm_submit_wait_two_in_flight(ctx, setup8k):
     assert ctx.msm_g1_wait(prev) == expect[-1]
     with pytest.raises(KzgNativeError):
         ctx.msm_g1_submit(setup8k, sets[0], 8193)               # more scalars than bases (src/polynomial.rs:201-205)
+    # device-resident scalars, both lanes busy at once
+    import torch
+    devs = [torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda() for s in (sets[0], sets[3])]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        ta = ctx.msm_g1_submit_dev(setup8k, devs[0].data_ptr(), sizes[0])
+        tb = ctx.msm_g1_submit_dev(setup8k, devs[1].data_ptr(), sizes[3])
+        assert ctx.msm_g1_wait(tb) == expect[3]                  # collecting the newer one first is allowed
+        assert ctx.msm_g1_wait(ta) == expect[0]
 
 
 def test_peer_exchange_single_rank_and_dead_peer():
