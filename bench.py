@@ -32,9 +32,10 @@ SEED = 0xC3
 MAC_PER_FQ_MUL = 300          # 12x12 product + 12x12+12 reduction
 MAC_PER_BUCKET_ADD = 3000     # XYZZ += affine: 8M + 2S = 10 Fq multiplications
 CANONICAL_MAC_PER_POINT = 48000  # c = 16: 16 windows x 3000 (SURVEY §8d canonical figure)
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add<true> launch at n = 2^20, c = 16, from the
-# ncu --set full capture summarised in profiles/prof_seg_add_r01_summary.txt (bytes per launch)
-TRAFFIC_NCU = 3.728110e9 + 824.405248e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add<true> launch at n = 2^20, c = 16, table on the
+# 128-byte pitch, from the ncu capture summarised in profiles/prof_seg_add_r01j_summary.txt (bytes per launch;
+# 3.728e9 + 0.824e9 on the 96-byte pitch, profiles/prof_seg_add_r01_summary.txt)
+TRAFFIC_NCU = 2.707788288e9 + 0.814427904e9
 
 
 def _clock_sampler(stop, samples, device_index):
@@ -140,6 +141,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     ctx = pkg.Context(local)
+    ctx.set_option("lanes", args.lanes)
 
     n_total = 1 << LOG_N
     per = n_total // world
@@ -149,6 +151,7 @@ def run_ours(args):
     setup.prepare_msm(args.window)
     ctx.sync()
     table_s = time.perf_counter() - t0
+    plan = setup.msm_plan(per)
 
     host = torch.from_numpy(synthetic.scalar_stream(SEED, per, start=first)).pin_memory()
     scal_dev = host.to(dev)
@@ -184,17 +187,20 @@ def run_ours(args):
         return step_dev()
 
     def two_in_flight(k, submit):
-        # submit / wait with two calls in flight (consecutive tickets run on the two lanes of the context): every
-        # step is a complete MSM whose 48-byte result is read back; the copy and the front of step i+1 overlap the
-        # latency-bound bucket reduction of step i
-        prev, out = None, None
+        # submit / wait with `lanes` calls in flight (ticket t runs on lane t mod lanes of the context): every step is a
+        # complete MSM whose 48-byte result is read back; the copy and the bulk kernels of one step overlap the
+        # latency-bound phases (inversion chains, bucket reduction) of the others
+        from collections import deque
+        q, out = deque(), None
         for _ in range(k):
-            t = submit()
-            if prev is not None:
-                out = ctx.msm_g1_wait(prev)
+            if len(q) == args.lanes:
+                out = ctx.msm_g1_wait(q.popleft())
                 assert out == r_ref[0], "a pipelined step returned a different commitment"
-            prev = t
-        return ctx.msm_g1_wait(prev)
+            q.append(submit())
+        while q:
+            out = ctx.msm_g1_wait(q.popleft())
+            assert out == r_ref[0], "a pipelined step returned a different commitment"
+        return out
 
     def steps_dev_pipelined(k):
         if world == 1:
@@ -204,6 +210,8 @@ def run_ours(args):
     def steps_e2e_pipelined(k):
         return two_in_flight(k, lambda: ctx.msm_g1_submit(setup, host.data_ptr(), per))
 
+    wall_ms = [0.0]     # host clock of the last timed region (max over ranks), reported beside the device time
+
     def timed_block(fn_k, steps):
         barrier()
         ctx.timer_start()
@@ -212,11 +220,15 @@ def run_ours(args):
         ms_dev = ctx.timer_stop()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        ms = ms_dev if world == 1 else wall
+        # device time: CUDA events on the engine stream (every lane joins it before the stop event; the peer exchange
+        # and the NCCL all-gather are enqueued on it too), max over ranks
+        ms = ms_dev
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms = float(t[0].item())
+            wall = float(t[1].item())
+        wall_ms[0] = wall
         return ms, out
 
     def barrier():
@@ -235,13 +247,13 @@ def run_ours(args):
         ms_dev = ctx.timer_stop()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        # multi-rank steps interleave two streams (ctx + NCCL): the host clock between device-wide
-        # synchronisations covers both; at N = 1 the CUDA-event time on the ctx stream is used.
-        ms = ms_dev if world == 1 else wall
+        ms = ms_dev                                # CUDA events on the engine stream, max over ranks
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms = float(t[0].item())
+            wall = float(t[1].item())
+        wall_ms[0] = wall
         return ms, out
 
     r_ref = [None]
@@ -250,7 +262,7 @@ def run_ours(args):
     r_ref[0] = r_dev
     pipelined = world == 1 or use_p2p
     if pipelined:
-        steps_dev_pipelined(max(2, args.warmup))
+        steps_dev_pipelined(max(2 * args.lanes, args.warmup))
 
     stop, samples = threading.Event(), []
     th = threading.Thread(target=_clock_sampler, args=(stop, samples, local), daemon=True)
@@ -263,6 +275,7 @@ def run_ours(args):
     if pipelined:                                            # two calls in flight: the headline throughput
         ms_total, r_pipe = timed_block(steps_dev_pipelined, args.steps)
         assert r_pipe == r_dev, "pipelined and one-at-a-time results differ"
+    wall_total = wall_ms[0]
     acc_ms, dom_ms = [], []
     for _ in range(min(args.steps, 5)):   # per-launch durations, CUDA events on the stream the kernels run on
         step_dev()
@@ -274,7 +287,7 @@ def run_ours(args):
     ms_e2e, r_e2e = timed(step_e2e, args.steps)
     ms_e2e_sync = ms_e2e
     if world == 1:
-        steps_e2e_pipelined(2)
+        steps_e2e_pipelined(2 * args.lanes)
         ms_e2e, r_pipe = timed_block(steps_e2e_pipelined, args.steps)
         assert r_pipe == r_e2e, "pipelined and synchronous host-buffer results differ"
     stop.set()
@@ -301,10 +314,10 @@ def run_ours(args):
         from ctypes import c_int
         acc = sorted(acc_ms)[len(acc_ms) // 2]
         dom = sorted(dom_ms)[len(dom_ms) // 2]
-        windows = setup_windows(ctx, setup, per, args.window)
+        windows = plan                                  # kzg_msm_plan: what the engine actually uses
         adds = windows["W"] * per                       # bucket additions of the whole phase
-        tree = adds >= (1 << 21)                        # msm_bucket's rule for the affine halving rounds
-        rounds = max(0, min(6, adds.bit_length() - 21))   # msm.cu auto_tree_rounds
+        rounds = windows["rounds"]                      # affine halving rounds (msm.cu auto_tree_rounds)
+        tree = rounds > 0
         dom_adds = adds // 2 if tree else adds          # round 1 pairs up all entries: half of the additions
         dom_name = "k_seg_add<true> (round-1 pair additions of the affine halving, msm_tree.cu)" if tree else "k_bucket_acc"
         achieved = dom_adds * MAC_PER_BUCKET_ADD / (dom * 1e-3)
@@ -315,7 +328,7 @@ def run_ours(args):
         cpu_val, cpu_dt = cpu_baseline(cpu_points, threads) if world == 1 else (None, None)
         line = {
             "metric": "kzg_commit_msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": wall_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32-limb modular integer (Fq 381-bit, Fr 255-bit)",
             "data": "synthetic",
             "config": {"workload": f"single G1 commit-MSM n=2^{LOG_N} (BASELINE config C3), uniform scalars U(0xC3,i), "
@@ -324,18 +337,18 @@ def run_ours(args):
                        "exchange": ("none" if world == 1 else "peer stores over NVLink + fold + compress in one kernel "
                                     "(k_exchange_combine)" if use_p2p else "NCCL all-gather of 192-byte partials + fold kernel"),
                        "l2": "inputs larger than L2 (table "
-                       f"{windows['W'] * per * 96 / 2**20:.0f} MiB + scalars {per * 32 / 2**20:.0f} MiB per GPU)",
+                       f"{windows['W'] * per * windows['table_pitch'] / 2**20:.0f} MiB + scalars {per * 32 / 2**20:.0f} MiB per GPU)",
                        "precomputed_table_s": round(table_s, 3),
-                       "calls_in_flight": 2 if pipelined else 1,
-                       "step": ("one complete MSM (48-byte result read back); steps are submitted two deep "
-                                "(kzg_msm_g1_submit_dev / _wait), so the front of step i+1 overlaps the bucket reduction of step i"
+                       "calls_in_flight": args.lanes if pipelined else 1,
+                       "step": (f"one complete MSM (48-byte result read back); steps are submitted {args.lanes} deep "
+                                "(kzg_msm_g1_submit_dev / _wait), so the bulk kernels of one step overlap the latency-bound phases of the others"
                                 if pipelined else "one complete MSM, one call at a time")},
             "one_call_at_a_time": {"value": n_total / (ms_single / args.steps * 1e-3), "unit": "points/s",
                                    "ms_per_step": ms_single / args.steps},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": per * 32 * world,
                     "d2h_bytes_per_step": 48, "ms_per_step": ms_e2e / args.steps,
-                    "call": ("kzg_msm_g1_submit / kzg_msm_g1_wait, two calls in flight (copy of step i+1 beside the kernels "
-                             "of step i)" if world == 1 else "host -> device copy + partial MSM + all-gather + combine per step"),
+                    "call": (f"kzg_msm_g1_submit / kzg_msm_g1_wait, {args.lanes} calls in flight (copy of step i+1 beside the kernels "
+                             "of the older steps)" if world == 1 else "host -> device copy + partial MSM + all-gather + combine per step"),
                     "one_call_at_a_time": {"value": n_total / (ms_e2e_sync / args.steps * 1e-3), "unit": "points/s",
                                            "ms_per_step": ms_e2e_sync / args.steps, "call": "kzg_msm_g1"}},
             "gpu_launches": int(launches),
@@ -363,7 +376,7 @@ def run_ours(args):
                 "canonical_frac": (n_total / world) * CANONICAL_MAC_PER_POINT / (ms_step * 1e-3) / imad_peak,
                 "traffic": TRAFFIC_NCU if tree and world == 1 else None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add<true> launch (the dominant "
-                                "kernel), profiles/prof_seg_add_r01_summary.txt"},
+                                "kernel), profiles/prof_seg_add_r01j_summary.txt"},
         }
         line["other_configs"] = extra
         if blob is not None:
@@ -484,7 +497,7 @@ def blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, blobs_total, 
     same = bytes(commits.cpu().numpy().tobytes()) == bytes(out_c.numpy().tobytes()) and \
         bytes(proofs.cpu().numpy().tobytes()) == bytes(out_p.numpy().tobytes())
     setup.close()
-    W = (256 + fixed_window - 1) // fixed_window
+    W = (255 + fixed_window - 1) // fixed_window   # windows_for (csrc/engine.cuh)
     return {"metric": "blob_commit_plus_proof_per_s", "value": blobs_total / (ms_dev * 1e-3), "unit": "blobs/s",
             "ms_per_batch": ms_dev, "e2e": {"value": blobs_total / (ms_e2e * 1e-3), "unit": "blobs/s", "ms_per_batch": ms_e2e,
                                             "h2d_bytes_per_batch": 2 * blobs_total * n * 32 + blobs_total * 32,
@@ -493,12 +506,6 @@ def blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, blobs_total, 
                        "fixed_base_window_bits": fixed_window, "lookups_per_coefficient": W,
                        "table_gib": round(n * W * (1 << (fixed_window - 1)) * 96 / 2**30, 2), "table_build_s": round(table_s, 2)},
             "dev_equals_e2e": bool(same), "scaling": "weak" if world > 1 else "n/a"}
-
-
-def setup_windows(ctx, setup, n, requested):
-    """window geometry actually used (mirrors auto_msm_window / windows_for in csrc/setup.cu)."""
-    c = requested if requested else 16   # auto_msm_window(n >= 2^17) == 16
-    return {"c": c, "W": (256 + c - 1) // c}
 
 
 def main():
@@ -510,6 +517,8 @@ def main():
     ap.add_argument("--window", type=int, default=int(os.environ.get("KZG_WINDOW", "0")))
     ap.add_argument("--exchange", default=os.environ.get("KZG_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
                     help="multi-GPU exchange of the partial sums: fused peer-memory kernel (default) or NCCL all-gather")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("KZG_LANES", "4")),
+                    help="MSM calls in flight per GPU for the headline throughput (1..4)")
     ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BLOBS", "4096")),
                     help="size of the secondary blob batch (0 = skip)")
     ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "15")))

@@ -85,6 +85,9 @@ int32_t kzg_setup_import_g1(kzg_ctx* ctx, const uint8_t* g1_c48, uint64_t n, kzg
 int32_t kzg_setup_export_g1(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count,
                             uint8_t* out_c48);
 uint64_t kzg_setup_len(const kzg_setup* s);
+/* Geometry the bucket MSM uses for n scalars over this setup (for reports; needs kzg_setup_prepare_msm first):
+ * plan = { window_bits c, windows W = ceil(255/c), buckets 2^(c-1), affine halving rounds, table pitch in bytes }. */
+int32_t kzg_msm_plan(const kzg_ctx* ctx, const kzg_setup* s, uint64_t n, int32_t plan[5]);
 /* G2 half of SetupArtifact (src/trusted_setup.rs:31-35, 64-72): [s^i]G2 for items 0..count of the setup
  * (count <= len; the reference carries one per item, verify_proof reads only item 1), kept on the device
  * as 96-byte compressed points = Serialize for G2Point (src/curves.rs:260-271). */
@@ -128,14 +131,14 @@ int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32
 
 /* the same call split in two, for callers that commit one polynomial after another (the reference's benches
  * and CLI do: src/polynomial.rs:200-215 called in a loop): submit returns once the work is queued, wait blocks
- * for the 48-byte result.  At most TWO tickets may be outstanding; the host->device copy of the newer call
- * overlaps the kernels of the older one.  `scalars_le32` must stay valid (and should be page-locked for the copy
+ * for the 48-byte result.  At most L tickets may be outstanding (L = option "lanes", default 4 = the most; a
+ * submit beyond that fails with KZG_E_BAD_ARG); the host->device copy of a newer call overlaps the kernels of the older ones.  `scalars_le32` must stay valid (and should be page-locked for the copy
  * to be asynchronous) until its ticket has been waited for. */
 int32_t kzg_msm_g1_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n,
                           int32_t* ticket);
 int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]);
-/* Consecutive tickets run on two internal lanes (own streams and scratch memory) of the context, so the copy and the
- * first kernels of the newer call also overlap the latency-bound bucket reduction of the older one.  Variant with
+/* Ticket t runs on internal lane t mod L (own streams and scratch memory) of the context, so the copy and the bulk
+ * kernels of one call also overlap the latency-bound phases (inversion chains, bucket reduction) of the others.  Variant with
  * the scalars already in device memory (ready before the call: the engine does not know the producer's stream): */
 int32_t kzg_msm_g1_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,
                               int32_t* ticket);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "kzg_setup_import_g1": (_i32, [_vp, _vp, _u64, C.POINTER(_vp)]),
     "kzg_setup_export_g1": (_i32, [_vp, _vp, _u64, _u64, _vp]),
     "kzg_setup_len": (_u64, [_vp]),
+    "kzg_msm_plan": (_i32, [_vp, _vp, _u64, C.POINTER(_i32)]),
     "kzg_setup_generate_g2": (_i32, [_vp, _vp, _vp, _u64]),
     "kzg_setup_import_g2": (_i32, [_vp, _vp, _vp, _u64]),
     "kzg_setup_export_g2": (_i32, [_vp, _vp, _u64, _u64, _vp]),

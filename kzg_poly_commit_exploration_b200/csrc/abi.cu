@@ -142,7 +142,7 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
     if (!ctx->p2p_box[r]) continue;
     if (r == ctx->p2p_rank) cudaFree(ctx->p2p_box[r]); else cudaIpcCloseMemHandle(ctx->p2p_box[r]);
   }
-  if (ctx->lane1) kzg_ctx_destroy(ctx->lane1);
+  for (int l = 1; l < KZG_MAX_LANES; l++) if (ctx->lane[l]) kzg_ctx_destroy(ctx->lane[l]);
   if (ctx->gtable) cudaFree(ctx->gtable);
   if (ctx->g2table) cudaFree(ctx->g2table);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -159,7 +159,7 @@ const char* kzg_last_error(const kzg_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int32_t kzg_ctx_sync(kzg_ctx* ctx) {
   DeviceGuard g(ctx->device);
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->lane1) KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->lane1->stream));
+  for (int l = 1; l < KZG_MAX_LANES; l++) if (ctx->lane[l]) KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->lane[l]->stream));
   update_timers(ctx);
   return KZG_OK;
 }
@@ -172,9 +172,10 @@ int32_t kzg_ctx_timer_start(kzg_ctx* ctx) {
 
 int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
   DeviceGuard g(ctx->device);
-  if (ctx->lane1) {     // the interval ends when BOTH lanes are done
-    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->lane1->ev_t[1], ctx->lane1->stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane1->ev_t[1], 0));
+  for (int l = 1; l < KZG_MAX_LANES; l++) {     // the interval ends when EVERY lane is done
+    if (!ctx->lane[l]) continue;
+    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->lane[l]->ev_t[1], ctx->lane[l]->stream));
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane[l]->ev_t[1], 0));
   }
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_t[1], ctx->stream));
   KZG_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_t[1]));
@@ -182,7 +183,11 @@ int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
   return KZG_OK;
 }
 
-uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) { return ctx->launches + (ctx->lane1 ? ctx->lane1->launches : 0); }
+uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) {
+  uint64_t c = ctx->launches;
+  for (int l = 1; l < KZG_MAX_LANES; l++) if (ctx->lane[l]) c += ctx->lane[l]->launches;
+  return c;
+}
 
 void* kzg_ctx_stream(const kzg_ctx* ctx) { return ctx ? reinterpret_cast<void*>(ctx->stream) : nullptr; }
 
@@ -207,6 +212,10 @@ int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "tree_min_rows") ctx->opt_tree_min_rows = (int)value;
   else if (n == "tree_chunk_rows") ctx->opt_tree_chunk_rows = (int)value;
   else if (n == "tree_min_pairs") ctx->opt_tree_min_pairs = value;
+  else if (n == "lanes") {
+    if (ctx->lanes_in_use) return fail(ctx, KZG_E_BAD_ARG, "the number of lanes is fixed once a call has been submitted");
+    ctx->opt_lanes = (int)std::min<int64_t>(KZG_MAX_LANES, std::max<int64_t>(1, value));
+  }
   else if (n == "heavy_cap") ctx->opt_heavy_cap = (int)std::max<int64_t>(1, value);
   else return fail(ctx, KZG_E_BAD_ARG, "unknown option");
   return KZG_OK;
@@ -324,6 +333,14 @@ int32_t kzg_setup_export_g2(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, ui
 
 uint64_t kzg_setup_g2_len(const kzg_setup* s) { return s ? s->g2_n : 0; }
 
+int32_t kzg_msm_plan(const kzg_ctx* ctx, const kzg_setup* s, uint64_t n, int32_t plan[5]) {
+  if (!ctx || !s || !plan || !s->msm_c) return KZG_E_BAD_ARG;
+  plan[0] = s->msm_c; plan[1] = s->msm_w; plan[2] = 1 << (s->msm_c - 1);
+  plan[3] = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds((uint64_t)s->msm_w * n);
+  plan[4] = (int32_t)MSM_TAB_PITCH;
+  return KZG_OK;
+}
+
 void kzg_setup_destroy(kzg_setup* s) {
   if (!s) return;
   DeviceGuard g(s->ctx->device);
@@ -377,10 +394,11 @@ int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32
   return kzg_msm_g1_dev(ctx, s, d, n, out_c48);
 }
 
-// ---- two calls in flight -------------------------------------------------------------------------------------------
-// Even tickets run on the context itself, odd tickets on a hidden sibling context of the same device (own streams, own
-// scratch): the host->device copy AND the front of call k+1 overlap the latency-bound tail of call k (bucket
-// reduction: a few hundred warps for ~0.6 ms), which is worth 13 % at n = 2^20 and 30 % at n = 2^17.
+// ---- several calls in flight ----------------------------------------------------------------------------------------
+// Ticket t runs on lane t mod L (L = option "lanes", default and at most KZG_MAX_LANES = 4): lane 0 is the context itself,
+// the others are hidden sibling contexts of the same device (own streams, own scratch).  The host->device copy and the
+// bulk kernels of one call overlap the latency-bound phases of the others (the inversion chain of every halving round,
+// the bucket reduction: a few hundred warps for ~0.6 ms); two lanes are worth 13 % at n = 2^20 and 30 % at n = 2^17.
 static void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
   dst->opt_msm_window = src->opt_msm_window; dst->opt_fixed_window = src->opt_fixed_window;
   dst->opt_reduce_chunk = src->opt_reduce_chunk; dst->opt_heavy_cap = src->opt_heavy_cap; dst->opt_acc_split = src->opt_acc_split;
@@ -391,14 +409,16 @@ static void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
 }
 
 static int32_t lane_of(kzg_ctx* ctx, uint32_t ticket, kzg_ctx** lane) {
+  if (!ctx->lanes_in_use) ctx->lanes_in_use = std::min(KZG_MAX_LANES, std::max(1, ctx->opt_lanes));
+  const int l = (int)(ticket % (uint32_t)ctx->lanes_in_use);
   *lane = ctx;
-  if (!(ticket & 1)) return KZG_OK;
-  if (!ctx->lane1) {
-    int32_t st = kzg_ctx_create(&ctx->lane1, ctx->device);
-    if (st != KZG_OK) return fail(ctx, st, "could not create the second lane of the submission queue");
+  if (l == 0) return KZG_OK;
+  if (!ctx->lane[l]) {
+    int32_t st = kzg_ctx_create(&ctx->lane[l], ctx->device);
+    if (st != KZG_OK) return fail(ctx, st, "could not create another lane of the submission queue");
   }
-  copy_options(ctx->lane1, ctx);
-  *lane = ctx->lane1;
+  copy_options(ctx->lane[l], ctx);
+  *lane = ctx->lane[l];
   return KZG_OK;
 }
 
@@ -411,10 +431,10 @@ static int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scala
   if (sharded && !ctx->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
   DeviceGuard g(ctx->device);
   const uint32_t t = ctx->next_ticket;
-  kzg_ctx::Pending& q = ctx->pending[t & 1];
-  if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "two calls are already in flight: wait for the older ticket first");
   kzg_ctx* lane;
   KZG_TRY(lane_of(ctx, t, &lane));
+  kzg_ctx::Pending& q = ctx->pending[t % (uint32_t)ctx->lanes_in_use];
+  if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "every lane has a call in flight: wait for the oldest ticket first");
   if (!s->msm_tab && !(s->fix_tab && n <= s->fix_n)) {      // built once, on the main lane, before any lane reads it
     KZG_TRY(ensure_msm_table(ctx, s));
     KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -466,9 +486,9 @@ int32_t kzg_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const vo
 
 int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
   if (!ctx || !out_c48 || ticket < 0) return KZG_E_BAD_ARG;
-  kzg_ctx::Pending& q = ctx->pending[(uint32_t)ticket & 1];
-  const uint32_t t = (uint32_t)ticket;
-  if (!q.busy || (t + 1 != ctx->next_ticket && t + 2 != ctx->next_ticket))
+  const uint32_t t = (uint32_t)ticket, L = (uint32_t)std::max(1, ctx->lanes_in_use);
+  kzg_ctx::Pending& q = ctx->pending[t % L];
+  if (!q.busy || ctx->next_ticket - t < 1 || ctx->next_ticket - t > L)
     return fail(ctx, KZG_E_BAD_ARG, "no call in flight under this ticket");
   DeviceGuard g(ctx->device);
   KZG_CUDA_OK(ctx, cudaEventSynchronize(q.done));

@@ -53,6 +53,7 @@ k_fixed_batch(const uint8_t* __restrict__ scalars, uint64_t n, uint64_t stride, 
       k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
     }
     fr_canon_reduce(k);
+    const bool flip = fr_fold_half(k);
     uint32_t carry = 0;
     const G1Affine* row = fix + (((size_t)i * W) << (c - 1));
 #pragma unroll 1
@@ -62,7 +63,7 @@ k_fixed_batch(const uint8_t* __restrict__ scalars, uint64_t n, uint64_t stride, 
       if (negd) { d = (1u << c) - d; carry = 1; } else carry = 0;
       if (d != 0) {
         G1Affine p; ld_affine_b(p, row + ((size_t)j << (c - 1)) + (d - 1));
-        madd(acc, p, negd);
+        madd(acc, p, negd != flip);
       }
     }
   }

@@ -41,13 +41,14 @@ __device__ __forceinline__ void digits_of(const uint8_t* scalars, uint64_t row, 
   k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w;
   k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
   fr_canon_reduce(k);
+  const bool flip = fr_fold_half(k);
   const uint32_t half = 1u << (c - 1);
   uint32_t carry = 0;
   for (int j = 0; j < W; j++) {
     uint32_t d = window_tr(k.v, j * c, c) + carry;
     bool negd = d > half;
     if (negd) { d = (1u << c) - d; carry = 1; } else carry = 0;
-    dig[j] = d | (negd ? 0x80000000u : 0u);
+    dig[j] = d | ((negd != flip) ? 0x80000000u : 0u);
   }
 }
 

@@ -21,8 +21,9 @@ enum ScratchSlot {
 };
 
 constexpr int KZG_MAX_PEERS = 32;
-constexpr int KZG_P2P_DEPTH = 4;      // mailbox slots per peer: with at most two calls in flight per rank, call k + 2 may
-                                     // overwrite the slot of call k - 2, which every rank has finished reading (msm_tail.cu)
+constexpr int KZG_MAX_LANES = 4;      // calls in flight per context (kzg_msm_g1_submit*): one lane (streams + scratch) each
+constexpr int KZG_P2P_DEPTH = 2 * KZG_MAX_LANES;   // mailbox slots per peer: with at most L calls in flight per rank, call
+                                     // k + L may overwrite the slot of call k - L, which every rank has finished reading (msm_tail.cu)
 }  // namespace kzg
 
 struct kzg_ctx {
@@ -52,14 +53,14 @@ struct kzg_ctx {
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
   int opt_inv_top_fan = 4;             // values per thread in the fused top kernel (4 or 8; measured: 4)
   int64_t opt_inv_top = 1 << 18;       // batch inversion: values left for the fused top kernel
-  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (log2(entries) - 20, 0..6)
+  int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (log2(entries) - 19, 0..6)
   int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_tree_k = 0;                  // pairs per thread in the halving rounds: 0 = auto (fill the last wave), else 8..16
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
   int opt_acc_minblocks = 3;           // resident blocks per SM the accumulate kernel is compiled for
   int sm_count = 148;
-  // two-deep submission queue of kzg_msm_g1_submit / kzg_msm_g1_wait (host->device copy of call k+1 beside call k)
+  // submission queue of kzg_msm_g1_submit / kzg_msm_g1_wait (host->device copy of call k+1 beside call k)
   struct Pending {
     void* scalars = nullptr; size_t cap = 0;   // device staging of this slot
     void* result = nullptr;                    // device: one G1Xyzz + 48 compressed bytes + status word
@@ -68,10 +69,13 @@ struct kzg_ctx {
     cudaEvent_t copied = nullptr, done = nullptr;
     int32_t status = 0;
     bool busy = false;
-  } pending[2];
+  } pending[kzg::KZG_MAX_LANES];
   uint32_t next_ticket = 0;
-  kzg_ctx* lane1 = nullptr;            // odd tickets run on a hidden sibling context (own streams and scratch) so that the
-                                       // latency-bound tail of one call overlaps the bulk kernels of the next
+  int opt_lanes = 4;                   // calls in flight (1 .. KZG_MAX_LANES); fixed once the first ticket is out
+  int lanes_in_use = 0;                // opt_lanes latched by the first submit
+  kzg_ctx* lane[kzg::KZG_MAX_LANES] = {};   // ticket t runs on lane t mod L; lane 0 is the context itself, the others are hidden
+                                       // sibling contexts (own streams and scratch), so that the latency-bound phases of one
+                                       // call (inversion chains, bucket reduction) overlap the bulk kernels of the others
   // multi-GPU exchange over peer memory (msm_tail.cu k_exchange_combine): box[r] = rank r's mailbox as seen from here
   int p2p_world = 0, p2p_rank = 0;
   bool p2p_connected = false;
@@ -88,7 +92,10 @@ struct kzg_setup {
   uint64_t g2_n = 0;
   // folded-window table for the bucket MSM: tab[j*n + i] = 2^(c*j) * P_i ; tab window 0 == bases
   int msm_c = 0, msm_w = 0;
-  kzg::G1Affine* msm_tab = nullptr;    // [(w) * n]  (window 0 aliases nothing: full copy kept for simple indexing)
+  // Entries sit on a 128-byte pitch (kzg::MSM_TAB_PITCH): the round-1 gathers of the bucket accumulation fetch
+  // whole 128-byte DRAM lines whatever they ask for, and a 96-byte pitch makes one entry in two straddle two lines
+  // (ncu: 166 B of DRAM traffic per 48-byte x read); on the 128-byte pitch every random point read is exactly one line.
+  char* msm_tab = nullptr;             // [(w) * n] x 128 B: G1Affine + 32 B of padding
   // fixed-base lookup table: fix[((i*w + j) << (c-1)) + d-1] = d * 2^(c*j) * P_i
   int fix_c = 0, fix_w = 0;
   uint64_t fix_n = 0;
@@ -126,12 +133,18 @@ inline int32_t fail(kzg_ctx* ctx, int32_t st, const char* msg) {
   return st;
 }
 
+// pitch of the folded-window MSM table in bytes (one G1Affine per 128-byte DRAM line)
+constexpr uint32_t MSM_TAB_PITCH = 128;
+constexpr uint32_t DENSE_PITCH = 96;   // sizeof(G1Affine): the dense point arrays between the halving rounds
+
 // ---- window geometry ------------------------------------------------------------------
-inline int windows_for(int c) { return (256 + c - 1) / c; }
-// signed-digit recoding needs the top window to absorb a carry: with r < 2^255 and
-// W = ceil(256/c) windows the top window holds at most (255 - c*(W-1)) < c bits, so the
-// carry never leaves it.
+inline int windows_for(int c) { return (255 + c - 1) / c; }
+// The recoders first fold the scalar into [0, (r-1)/2] (fr_fold_half: k -> r - k with every digit's sign flipped), so
+// k < 2^254.  Signed-digit recoding needs the top window to absorb a carry: with W = ceil(255/c) windows the top
+// window holds at most 254 - c*(W-1) <= c - 1 bits, so digit + carry <= 2^(c-1) and the carry never leaves it
+// (SURVEY A.2 with one bit less).  c = 17 needs 15 windows, c = 15 needs 17, c = 16 still 16.
 int auto_msm_window(uint64_t n);
+int auto_tree_rounds(uint64_t entries);   // msm.cu: affine halving rounds for W*n bucket entries
 
 // ---- poly.cu (K4: Horner evaluation + quotient scan) -----------------------------------
 // coeffs_dev: blobs x n x 32 B canonical-or-not LE; z_dev: blobs x 32 B; outputs canonical.
@@ -191,7 +204,7 @@ int32_t batch_invert_inplace(kzg_ctx* ctx, Fq* v, uint64_t N, Fq* ws, uint64_t t
 // ---- msm_tree.cu (K2') ----------------------------------------------------------------------
 // `rounds` halvings of every bucket's sorted entries in affine coordinates (shared inversions).  In: bucket
 // bounds start[0..M] over vals (table index | sign << 31).  Out: dense affine points + their bounds.
-int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const G1Affine* tab,
+int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const char* tab_pitched,
                         uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
                         const uint32_t** seg_out, const uint32_t** iota_out, uint64_t* entries_out);
 

@@ -238,6 +238,29 @@ KZG_HD void fr_canon_reduce(Fr& a) {
   }
 }
 
+// Halve the range of a canonical scalar before the signed-digit recoding: for k > (r-1)/2 continue with r - k and
+// flip the sign of every digit ([k]P = -[r-k]P).  Afterwards k < 2^254, so ceil(255/c) windows of c bits hold it
+// together with the top carry (windows_for, engine.cuh) - one window fewer when c divides 255 (c = 15, 17).
+// Returns true when the scalar was replaced by r - k.
+KZG_HD bool fr_fold_half(Fr& k) {
+  uint32_t t[8]; uint32_t br = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    uint64_t d = (uint64_t)KZG_C(FR_P)[j] - k.v[j] - br;
+    t[j] = (uint32_t)d; br = (uint32_t)(d >> 63);
+  }
+  br = 0;                       // r - k < k ?
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    uint64_t d = (uint64_t)t[j] - k.v[j] - br;
+    br = (uint32_t)(d >> 63);
+  }
+  if (!br) return false;
+#pragma unroll
+  for (int j = 0; j < 8; j++) k.v[j] = t[j];
+  return true;
+}
+
 // a > (q-1)/2 on the canonical value — decides the ZCash sign bit (src/curves.rs:106).
 KZG_HD bool fq_canon_gt_half(const Fq& a) {
   uint32_t br = 0;

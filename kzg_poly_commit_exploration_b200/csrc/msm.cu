@@ -2,7 +2,7 @@
 //
 // Replaces Polynomial::commit's loop (src/polynomial.rs:207-212): n x (256-bit blst_p1_mult +
 // blst_p1_add_or_double), i.e. O(255 n) group operations, by
-//   1. recode   : canonical scalar -> W = ceil(256/c) signed c-bit digits; digit d of
+//   1. recode   : canonical scalar, folded to min(k, r-k) -> W = ceil(255/c) signed c-bit digits; digit d of
 //                 window j for point i becomes the pair (bucket |d|-1, table index j*n+i | sign).
 //                 Windows are FOLDED: the setup holds 2^(c j) * P_i for every j (built once per
 //                 setup, setup.cu), so all W windows share one set of 2^(c-1) buckets and the
@@ -53,6 +53,7 @@ __global__ void k_recode(const uint8_t* __restrict__ scalars, uint64_t n, int c,
   if (i >= n) return;
   Fr k; ld_scalar(k, scalars + i * 32);
   fr_canon_reduce(k);
+  const bool flip = fr_fold_half(k);                       // k <- min(k, r - k): one bit less to recode
   const uint32_t half = 1u << (c - 1);
   uint32_t carry = 0;
   for (int j = 0; j < W; j++) {
@@ -60,7 +61,7 @@ __global__ void k_recode(const uint8_t* __restrict__ scalars, uint64_t n, int c,
     bool negd = d > half;
     if (negd) { d = (1u << c) - d; carry = 1; } else carry = 0;
     keys[(size_t)j * n + i] = d ? d - 1 : half;            // `half` = discard bucket for zero digits
-    vals[(size_t)j * n + i] = (uint32_t)((uint64_t)j * n_stride + i) | (negd ? 0x80000000u : 0u);
+    vals[(size_t)j * n + i] = (uint32_t)((uint64_t)j * n_stride + i) | ((negd != flip) ? 0x80000000u : 0u);
   }
 }
 
@@ -88,7 +89,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_bucket_acc(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
-             const G1Affine* __restrict__ tab, uint32_t nbuckets, uint32_t logT, uint32_t heavy_cap,
+             const char* __restrict__ tab, uint32_t pitch, uint32_t nbuckets, uint32_t logT, uint32_t heavy_cap,
              G1Xyzz* __restrict__ partials, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t b = t >> logT, k = t & ((1u << logT) - 1u);
@@ -106,18 +107,18 @@ k_bucket_acc(const uint32_t* __restrict__ start, const uint32_t* __restrict__ va
   uint32_t v = 0;
   if (lo < hi) {
     v = __ldg(vals + lo);
-    const G1Affine* np = tab + (v & 0x7FFFFFFFu);
-    prefetch_l2(np); prefetch_l2(reinterpret_cast<const char*>(np) + 95);
+    const char* np = tab + (size_t)(v & 0x7FFFFFFFu) * pitch;
+    prefetch_l2(np); prefetch_l2(np + 95);
   }
 #pragma unroll 1
   for (uint32_t i = lo; i < hi; i++) {
     uint32_t vc = v;
     if (i + 1 < hi) {
       v = __ldg(vals + i + 1);
-      const G1Affine* np = tab + (v & 0x7FFFFFFFu);
-      prefetch_l2(np); prefetch_l2(reinterpret_cast<const char*>(np) + 95);
+      const char* np = tab + (size_t)(v & 0x7FFFFFFFu) * pitch;
+      prefetch_l2(np); prefetch_l2(np + 95);
     }
-    G1Affine p; ld_affine_g(p, tab + (vc & 0x7FFFFFFFu));
+    G1Affine p; ld_affine_g(p, reinterpret_cast<const G1Affine*>(tab + (size_t)(vc & 0x7FFFFFFFu) * pitch));
     madd(acc, p, (vc >> 31) != 0);
   }
   partials[t] = acc;
@@ -130,7 +131,7 @@ constexpr int HEAVY_BLOCKS = 32;
 
 __global__ void __launch_bounds__(128)
 k_bucket_heavy(const uint32_t* __restrict__ start, const uint32_t* __restrict__ vals,
-               const G1Affine* __restrict__ tab, G1Xyzz* __restrict__ heavy_parts,
+               const char* __restrict__ tab, uint32_t pitch, G1Xyzz* __restrict__ heavy_parts,
                const uint32_t* __restrict__ heavy_list, const uint32_t* __restrict__ heavy_count) {
   __shared__ G1Xyzz sh[128];
   uint32_t nh = *heavy_count;
@@ -141,7 +142,7 @@ k_bucket_heavy(const uint32_t* __restrict__ start, const uint32_t* __restrict__ 
 #pragma unroll 1
     for (uint32_t k = s + blockIdx.x * blockDim.x + threadIdx.x; k < e; k += blockDim.x * HEAVY_BLOCKS) {
       uint32_t v = __ldg(vals + k);
-      G1Affine p; ld_affine_g(p, tab + (v & 0x7FFFFFFFu));
+      G1Affine p; ld_affine_g(p, reinterpret_cast<const G1Affine*>(tab + (size_t)(v & 0x7FFFFFFFu) * pitch));
       madd(acc, p, (v >> 31) != 0);
     }
     sh[threadIdx.x] = acc;
@@ -174,11 +175,14 @@ __global__ void k_set_inf(G1Xyzz* out, uint32_t count) {
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-// affine halving rounds by problem size (measured, profiles/sweep_tree_rounds_r01.txt): one per doubling of the
-// entry count from 2^21 entries on — 1 at 2^21 (n = 2^17), 4 at 2^24 (n = 2^20), at most 6
-static int auto_tree_rounds(uint64_t entries) {
+// affine halving rounds by problem size (measured, profiles/sweep_tree_rounds_r01.txt, sweep_lanes_r01.txt): one per
+// doubling of the entry count from 2^20 entries on - 2 at n = 2^17, 5 at n = 2^20 (c = 16), at most 6.  A round's
+// inversion chain is ~0.15 ms of latency; with several calls in flight (lanes) that latency is covered by the bulk
+// kernels of the other calls, so one round more than the single-call break-even pays (n = 2^20, 4 lanes: 5.60 -> 5.51 ms;
+// n = 2^17: 1.18 -> 1.10 ms) and costs a lone call < 1.5 %.
+int auto_tree_rounds(uint64_t entries) {
   int r = 0;
-  while (r < 6 && (entries >> (21 + r)) != 0) r++;
+  while (r < 6 && (entries >> (20 + r)) != 0) r++;
   return r;
 }
 
@@ -233,13 +237,17 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   // optional affine halving rounds (msm_tree.cu): the accumulate kernel then walks dense affine points
   const uint32_t* acc_start = reinterpret_cast<uint32_t*>(st);
   const uint32_t* acc_vals = reinterpret_cast<uint32_t*>(vb);
-  const G1Affine* acc_tab = s->msm_tab;
+  const char* acc_tab = s->msm_tab;            // table entries on the 128-byte pitch; dense 96-byte points after a round
+  uint32_t acc_pitch = MSM_TAB_PITCH;
   uint64_t acc_entries = total;
   int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds(total);
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (rounds > 0)
-    KZG_TRY(msm_tree_rounds(ctx, acc_start, acc_vals, acc_tab, half, total, rounds, &acc_tab, &acc_start, &acc_vals,
+  if (rounds > 0) {
+    const G1Affine* dense = nullptr;
+    KZG_TRY(msm_tree_rounds(ctx, acc_start, acc_vals, acc_tab, half, total, rounds, &dense, &acc_start, &acc_vals,
                             &acc_entries));
+    acc_tab = reinterpret_cast<const char*>(dense); acc_pitch = DENSE_PITCH;
+  }
 
   // threads per bucket: aim for ~2^18 accumulate threads
   uint32_t logT = 0;
@@ -255,7 +263,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
     else if (ctx->opt_acc_minblocks == 6) kern = k_bucket_acc<6>;
     if (rounds == 0) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
     kern<<<blocks_for((uint64_t)half << logT, 128), 128, 0, ctx->stream>>>(
-        acc_start, acc_vals, acc_tab, half, logT, heavy_cap,
+        acc_start, acc_vals, acc_tab, acc_pitch, half, logT, heavy_cap,
         reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
   }
   KZG_LAUNCHED(ctx);
@@ -265,7 +273,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
     void* hp;
     KZG_TRY(scratch_get(ctx, SCR_HEAVY_PARTS, heavy_max * HEAVY_BLOCKS * sizeof(G1Xyzz), &hp));
     k_bucket_heavy<<<dim3(HEAVY_BLOCKS, 16), 128, 0, ctx->stream>>>(
-        acc_start, acc_vals, acc_tab, reinterpret_cast<G1Xyzz*>(hp), heavy_list, heavy_count);
+        acc_start, acc_vals, acc_tab, acc_pitch, reinterpret_cast<G1Xyzz*>(hp), heavy_list, heavy_count);
     KZG_LAUNCHED(ctx);
     k_heavy_fold<<<8, 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(hp), logT, reinterpret_cast<G1Xyzz*>(parts),
                                              heavy_list, heavy_count);

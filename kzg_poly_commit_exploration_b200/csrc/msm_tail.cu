@@ -385,10 +385,10 @@ k_sum_coop(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ o
 // straight into rank r's mailbox (peer memory mapped through CUDA IPC, NVLink 5 / NVSwitch), publishes it with a
 // release store of the call's sequence number, then spins (acquire loads) on its own mailbox until all `world`
 // partials of this call have landed; the four warps fold them with cooperative additions and thread 0 converts to
-// affine and compresses.  Mailbox slots are KZG_P2P_DEPTH = 4 deep, indexed by the call number: a rank has at most
-// two calls in flight (submit k + 2 only after waiting for k), k completes on a rank only when EVERY rank has published
-// k, and a rank publishes k only after it finished k - 2; so when call k + 2 overwrites the slot of call k - 2 every
-// rank is done reading it.  A bounded spin turns a dead peer into an error instead of a hang.
+// affine and compresses.  Mailbox slots are KZG_P2P_DEPTH = 2 L deep (L = KZG_MAX_LANES), indexed by the call number: a
+// rank has at most L calls in flight (submit k + L only after waiting for k), k completes on a rank only when EVERY rank
+// has published k, and a rank publishes k only after it finished k - L; so when call k + L overwrites the slot of call
+// k - L every rank is done reading it.  A bounded spin turns a dead peer into an error instead of a hang.
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

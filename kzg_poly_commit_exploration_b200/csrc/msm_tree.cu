@@ -113,8 +113,11 @@ __device__ __forceinline__ PairRef pair_ref(const uint32_t* __restrict__ seg_in,
   PairRef r;
   if (R1) {
     const uint32_t v1 = __ldg(vals + e1), v2 = has2 ? __ldg(vals + e1 + 1) : 0u;
-    r.p1 = src + (v1 & 0x7FFFFFFFu); r.n1 = (v1 >> 31) != 0;
-    r.p2 = has2 ? src + (v2 & 0x7FFFFFFFu) : nullptr; r.n2 = (v2 >> 31) != 0;
+    // round 1 reads the folded-window table: one entry per 128-byte line (MSM_TAB_PITCH)
+    const char* tb = reinterpret_cast<const char*>(src);
+    r.p1 = reinterpret_cast<const G1Affine*>(tb + (size_t)(v1 & 0x7FFFFFFFu) * MSM_TAB_PITCH); r.n1 = (v1 >> 31) != 0;
+    r.p2 = has2 ? reinterpret_cast<const G1Affine*>(tb + (size_t)(v2 & 0x7FFFFFFFu) * MSM_TAB_PITCH) : nullptr;
+    r.n2 = (v2 >> 31) != 0;
   } else {
     r.p1 = src + e1; r.n1 = false;
     r.p2 = has2 ? src + e1 + 1 : nullptr; r.n2 = false;
@@ -191,7 +194,7 @@ k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const G1Affine* tab,
+int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const char* tab_pitched,
                         uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
                         const uint32_t** seg_out_p, const uint32_t** iota_out, uint64_t* entries_out) {
   const uint64_t top = (uint64_t)ctx->opt_inv_top;
@@ -223,7 +226,7 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   G1Affine* buf[2] = {reinterpret_cast<G1Affine*>(A), reinterpret_cast<G1Affine*>(B)};
 
   const uint32_t* seg_in = start_dev;
-  const G1Affine* src = tab;
+  const G1Affine* src = reinterpret_cast<const G1Affine*>(tab_pitched);   // round 1 indexes it by MSM_TAB_PITCH
   uint64_t bound = entries;
   for (int r = 0; r < rounds; r++) {
     bound = halve(bound);

@@ -186,6 +186,14 @@ __global__ void k_uncompress(const uint8_t* __restrict__ in, uint64_t n, G1Affin
   out[i] = a;
 }
 
+// dense [n] x 96 B  ->  [n] x 128 B pitch (one point per DRAM line); 8 threads per point, 16 bytes each
+__global__ void k_pitch_table(const uint4* __restrict__ in, uint64_t n, uint4* __restrict__ out) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i = t >> 3; uint32_t q = (uint32_t)t & 7u;
+  if (i >= n) return;
+  out[i * 8 + q] = q < 6 ? in[i * 6 + q] : make_uint4(0, 0, 0, 0);
+}
+
 __global__ void k_set_generator(G1Affine* out) { G1Affine g; g1_generator(g); out[0] = g; }
 
 // -----------------------------------------------------------------------------------------------
@@ -317,7 +325,11 @@ int auto_msm_window(uint64_t n) {
   // only a few bits funnel n / 2^t entries into a handful of buckets (the heavy path).  Prefer c = 16
   // (16 windows, 15-bit top window) for large n; scale down so that ~2^18 accumulate threads still get
   // >= 32 entries each for small n.
-  if (n >= (1ull << 17)) return 16;
+  // With the scalars folded to 254 bits (fr_fold_half) c = 15 needs 17 windows and c = 17 only 15; measured with the
+  // fold (profiles/sweep_lanes_r01.txt): at n = 2^20 c = 17 saves 1/16 of the additions but doubles the bucket
+  // reduction and ends up level (5.48 vs 5.51 ms); at n = 2^17 c = 15 wins (1.07 vs 1.10 ms).
+  if (n >= (1ull << 18)) return 16;
+  if (n >= (1ull << 17)) return 15;
   int best = 4; double best_cost = 1e300;
   for (int c = 4; c <= 16; c++) {
     int W = windows_for(c);
@@ -341,12 +353,26 @@ int32_t build_msm_table(kzg_ctx* ctx, kzg_setup* s, int c) {
   if (s->msm_tab) { cudaFree(s->msm_tab); s->msm_tab = nullptr; }
   int W = windows_for(c);
   if (s->n == 0) { s->msm_c = c; s->msm_w = W; return KZG_OK; }
-  G1Affine* tab = nullptr;
-  cudaError_t e = cudaMalloc(&tab, sizeof(G1Affine) * (size_t)W * s->n);
-  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, KZG_E_NOMEM, "cudaMalloc(msm table)"); }
-  int32_t st = fold_windows(ctx, s->bases, s->n, c, W, tab);
+  const uint64_t entries = (uint64_t)W * s->n;
+  G1Affine* dense = nullptr;     // built densely (each window is 2^c times the previous one), then spread to the pitch
+  char* tab = nullptr;
+  if (cudaMalloc(&dense, sizeof(G1Affine) * entries) != cudaSuccess ||
+      cudaMalloc(&tab, (size_t)MSM_TAB_PITCH * entries) != cudaSuccess) {
+    cudaGetLastError();
+    if (dense) cudaFree(dense);
+    return fail(ctx, KZG_E_NOMEM, "cudaMalloc(msm table)");
+  }
+  int32_t st = fold_windows(ctx, s->bases, s->n, c, W, dense);
+  if (st == KZG_OK) {
+    k_pitch_table<<<blocks_for(entries * 8, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense), entries,
+                                                                        reinterpret_cast<uint4*>(tab));
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) st = fail(ctx, KZG_E_CUDA, "k_pitch_table launch");
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dense);
+  if (st == KZG_OK && e != cudaSuccess) st = fail(ctx, KZG_E_CUDA, "msm table build");
   if (st != KZG_OK) { cudaFree(tab); return st; }
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   s->msm_tab = tab; s->msm_c = c; s->msm_w = W;
   return KZG_OK;
 }

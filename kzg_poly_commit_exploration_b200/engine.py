@@ -112,7 +112,7 @@ class Context:
         return bytes(o)
 
     def msm_g1_submit(self, setup: "Setup", scalars_le32, n: int | None = None) -> int:
-        """Queue one MSM (at most two in flight); the host buffer must outlive the matching msm_g1_wait."""
+        """Queue one MSM (at most `lanes` in flight, default 4); the host buffer must outlive the matching msm_g1_wait."""
         n = len(scalars_le32) // 32 if n is None else n
         t = C.c_int32(-1)
         self.check(N.lib().kzg_msm_g1_submit(self._h, setup._h, _ptr(scalars_le32), n, C.byref(t)))
@@ -212,6 +212,12 @@ class Setup:
 
     def __len__(self):
         return int(N.lib().kzg_setup_len(self._h))
+
+    def msm_plan(self, n: int) -> dict:
+        """window geometry and halving rounds the bucket MSM uses for n scalars (after prepare_msm)"""
+        p = (C.c_int32 * 5)()
+        self.ctx.check(N.lib().kzg_msm_plan(self.ctx._h, self._h, n, p))
+        return {"c": p[0], "W": p[1], "buckets": p[2], "rounds": p[3], "table_pitch": p[4]}
 
     def export_g1(self, first: int = 0, count: int | None = None) -> bytes:
         count = len(self) - first if count is None else count

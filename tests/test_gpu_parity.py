@@ -435,38 +435,49 @@ def test_sharded_partials_combine(ctx):
         st.close()
 
 
-def test_msm_submit_wait_two_in_flight(ctx, setup8k):
-    """kzg_msm_g1_submit / kzg_msm_g1_wait: same bytes as the one-shot call, whatever the interleaving."""
+@pytest.mark.parametrize("lanes", [1, 2, 3, 4])
+def test_msm_submit_wait_calls_in_flight(lanes):
+    """kzg_msm_g1_submit / kzg_msm_g1_wait with `lanes` calls in flight: same bytes as the one-shot call, whatever
+    the interleaving; one ticket more than there are lanes is refused."""
+    import kzg_poly_commit_exploration_b200 as pkg
     from kzg_poly_commit_exploration_b200._native import KzgNativeError
-    sizes = [3000, 17, 0, 8192, 1, 2999]
+    ctx = pkg.Context(0)
+    ctx.set_option("lanes", lanes)
+    setup = ctx.setup_generate(O.BENCH_SECRET_BE, 8192)
+    sizes = [3000, 17, 0, 8192, 1, 2999, 512, 4097]
     sets = [util.scalar_stream_bytes(0x51 + i, n) for i, n in enumerate(sizes)]
-    expect = [ctx.msm_g1(setup8k, s, n) for s, n in zip(sets, sizes)]
+    expect = [ctx.msm_g1(setup, s, n) for s, n in zip(sets, sizes)]
     assert expect[2] == O.g1_compress(None)
-    t0 = ctx.msm_g1_submit(setup8k, sets[0], sizes[0])
-    t1 = ctx.msm_g1_submit(setup8k, sets[1], sizes[1])
+    tickets = [ctx.msm_g1_submit(setup, sets[i], sizes[i]) for i in range(lanes)]
     with pytest.raises(KzgNativeError):
-        ctx.msm_g1_submit(setup8k, sets[2], sizes[2])          # two already in flight
-    assert ctx.msm_g1_wait(t0) == expect[0]
+        ctx.msm_g1_submit(setup, sets[lanes], sizes[lanes])     # every lane already has a call in flight
     with pytest.raises(KzgNativeError):
-        ctx.msm_g1_wait(t0)                                     # already collected
-    prev = t1
-    for i in range(2, len(sets)):
-        t = ctx.msm_g1_submit(setup8k, sets[i], sizes[i])
-        assert ctx.msm_g1_wait(prev) == expect[i - 1]
-        prev = t
-    assert ctx.msm_g1(setup8k, sets[0], sizes[0]) == expect[0]   # the one-shot call still works beside a pending ticket
-    assert ctx.msm_g1_wait(prev) == expect[-1]
+        ctx.set_option("lanes", 1)                              # fixed once a ticket is out
+    assert ctx.msm_g1_wait(tickets[0]) == expect[0]
     with pytest.raises(KzgNativeError):
-        ctx.msm_g1_submit(setup8k, sets[0], 8193)               # more scalars than bases (src/polynomial.rs:201-205)
-    # device-resident scalars, both lanes busy at once
+        ctx.msm_g1_wait(tickets[0])                             # already collected
+    pending = list(zip(tickets[1:], range(1, lanes)))
+    for i in range(lanes, len(sets)):                           # sliding window over the remaining inputs
+        pending.append((ctx.msm_g1_submit(setup, sets[i], sizes[i]), i))
+        t, j = pending.pop(0)
+        assert ctx.msm_g1_wait(t) == expect[j]
+    assert ctx.msm_g1(setup, sets[0], sizes[0]) == expect[0]    # the one-shot call still works beside pending tickets
+    for t, j in reversed(pending):                              # collecting newer tickets first is allowed
+        assert ctx.msm_g1_wait(t) == expect[j]
+    with pytest.raises(KzgNativeError):
+        ctx.msm_g1_submit(setup, sets[0], 8193)                 # more scalars than bases (src/polynomial.rs:201-205)
+    # device-resident scalars, every lane busy at once
     import torch
-    devs = [torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda() for s in (sets[0], sets[3])]
+    devs = [torch.frombuffer(bytearray(sets[i]), dtype=torch.uint8).cuda() for i in (0, 3, 5, 7)]
+    want = [expect[i] for i in (0, 3, 5, 7)]
+    ns = [sizes[i] for i in (0, 3, 5, 7)]
     torch.cuda.synchronize()
     for _ in range(3):
-        ta = ctx.msm_g1_submit_dev(setup8k, devs[0].data_ptr(), sizes[0])
-        tb = ctx.msm_g1_submit_dev(setup8k, devs[1].data_ptr(), sizes[3])
-        assert ctx.msm_g1_wait(tb) == expect[3]                  # collecting the newer one first is allowed
-        assert ctx.msm_g1_wait(ta) == expect[0]
+        ts = [ctx.msm_g1_submit_dev(setup, devs[k].data_ptr(), ns[k]) for k in range(lanes)]
+        for k in reversed(range(lanes)):
+            assert ctx.msm_g1_wait(ts[k]) == want[k]
+    setup.close()
+    ctx.close()
 
 
 def test_peer_exchange_single_rank_and_dead_peer():

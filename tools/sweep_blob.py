@@ -27,5 +27,5 @@ for c in cs:
     t0 = time.perf_counter(); step(); step(); ms = (time.perf_counter() - t0) * 500
     out = bytes(commits.cpu().numpy().tobytes()) + bytes(proofs.cpu().numpy().tobytes())
     if ref is None: ref = out
-    W = (256 + c - 1) // c
+    W = (255 + c - 1) // c
     print(f"c={c} W={W} table {n*W*(1<<(c-1))*96/2**30:.1f} GiB built in {tb:.2f}s: {ms:.1f} ms per {blobs} blobs = {blobs/ms*1e3:.0f} blobs/s same={out == ref}", flush=True)
