@@ -168,10 +168,13 @@ int32_t kzg_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_o
 int32_t kzg_p2p_connect(kzg_ctx* ctx, const uint8_t* handles);
 int32_t kzg_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,
                                uint8_t out_c48[48]);
-/* the same, two collective calls in flight (collect with kzg_msm_g1_wait); the ticket numbers are the collective's
- * sequence numbers, so every rank must issue the same sequence of submit calls on its context */
+/* the same with up to `lanes` collective calls in flight (collect with kzg_msm_g1_wait); the ticket numbers are the
+ * collective's sequence numbers, so every rank must issue the same sequence of submit calls on its context */
 int32_t kzg_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,
                                       int32_t* ticket);
+/* ... and with this rank's shard of the scalars in a HOST buffer (copied on the lane's copy stream, like kzg_msm_g1_submit) */
+int32_t kzg_msm_g1_sharded_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n,
+                                  int32_t* ticket);
 /* fold `count` partial sums (device) into one compressed point */
 int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count,
                            uint8_t out_c48[48]);

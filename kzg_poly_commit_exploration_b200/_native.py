@@ -57,6 +57,7 @@ SIGNATURES = {
     "kzg_msm_g1_wait": (_i32, [_vp, _i32, _vp]),
     "kzg_msm_g1_submit_dev": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(_i32)]),
     "kzg_msm_g1_sharded_submit_dev": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(_i32)]),
+    "kzg_msm_g1_sharded_submit": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(_i32)]),
     "kzg_msm_g1_partial_dev": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "kzg_g1_combine_dev": (_i32, [_vp, _vp, _u64, _vp]),
     "kzg_p2p_init": (_i32, [_vp, _i32, _i32, _vp]),

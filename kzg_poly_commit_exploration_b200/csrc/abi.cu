@@ -483,6 +483,9 @@ int32_t kzg_msm_g1_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scal
 int32_t kzg_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket) {
   return submit_common(ctx, s, scalars_dev, n, false, true, ticket);
 }
+int32_t kzg_msm_g1_sharded_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket) {
+  return submit_common(ctx, s, scalars_le32, n, true, true, ticket);
+}
 
 int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
   if (!ctx || !out_c48 || ticket < 0) return KZG_E_BAD_ARG;

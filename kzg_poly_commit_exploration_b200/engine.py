@@ -129,6 +129,13 @@ class Context:
         self.check(N.lib().kzg_msm_g1_sharded_submit_dev(self._h, setup._h, _ptr(scalars_dev), n, C.byref(t)))
         return t.value
 
+    def msm_g1_sharded_submit(self, setup: "Setup", scalars_le32, n: int | None = None) -> int:
+        """collective, this rank's shard of the scalars in a host buffer (kept alive until the matching msm_g1_wait)"""
+        n = len(scalars_le32) // 32 if n is None else n
+        t = C.c_int32(-1)
+        self.check(N.lib().kzg_msm_g1_sharded_submit(self._h, setup._h, _ptr(scalars_le32), n, C.byref(t)))
+        return t.value
+
     def msm_g1_wait(self, ticket: int) -> bytes:
         o = N.out(48)
         self.check(N.lib().kzg_msm_g1_wait(self._h, ticket, o))

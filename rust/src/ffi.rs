@@ -30,6 +30,17 @@ extern "C" {
     pub fn kzg_commit_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64, out_c48: *mut u8) -> i32;
     pub fn kzg_open_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64,
                           z_le32: *const u8, y_le32: *mut u8, proofs_c48: *mut u8) -> i32;
+    // precomputed tables (once per setup) and several commitments in flight (ticket t runs on lane t mod `lanes`)
+    pub fn kzg_ctx_set_option(ctx: *mut kzg_ctx, name: *const c_char, value: i64) -> i32;
+    pub fn kzg_setup_prepare_msm(ctx: *mut kzg_ctx, s: *mut kzg_setup, window_bits: i32) -> i32;
+    pub fn kzg_setup_prepare_fixed(ctx: *mut kzg_ctx, s: *mut kzg_setup, n_points: u64, window_bits: i32) -> i32;
+    pub fn kzg_msm_g1(ctx: *mut kzg_ctx, s: *const kzg_setup, scalars_le32: *const u8, n: u64, out_c48: *mut u8) -> i32;
+    pub fn kzg_msm_g1_submit(ctx: *mut kzg_ctx, s: *const kzg_setup, scalars_le32: *const u8, n: u64, ticket: *mut i32) -> i32;
+    pub fn kzg_msm_g1_wait(ctx: *mut kzg_ctx, ticket: i32, out_c48: *mut u8) -> i32;
+    // multi-GPU (one process per GPU): peer mailboxes over CUDA IPC, collective sharded MSM
+    pub fn kzg_p2p_init(ctx: *mut kzg_ctx, world: i32, rank: i32, handle_out: *mut u8) -> i32;
+    pub fn kzg_p2p_connect(ctx: *mut kzg_ctx, handles: *const u8) -> i32;
+    pub fn kzg_msm_g1_sharded_submit(ctx: *mut kzg_ctx, s: *const kzg_setup, scalars_le32: *const u8, n: u64, ticket: *mut i32) -> i32;
     // host-side G2 / pairing (only needed when blst is dropped altogether)
     pub fn kzg_g2_from_scalar(k_le: *const u8, out: *mut u8);
     pub fn kzg_g2_sub(a: *const u8, b: *const u8, out: *mut u8) -> i32;

@@ -36,14 +36,23 @@ def _worker(rank, world, port, n_total, ret):
     setup = ctx.setup_generate(synthetic.BENCH_SECRET_BE, count, first=first)
     scal = torch.from_numpy(synthetic.scalar_stream(0xC3, count, start=first)).to(torch.device(f"cuda:{rank}"))
     outs = [ctx.msm_g1_sharded_dev(setup, scal.data_ptr(), count) for _ in range(5)]   # every mailbox slot, back to back
-    # two collective calls in flight on the two lanes of the context
-    prev = None
+    # four collective calls in flight (one per lane of the context), 19 calls: the 8-deep mailboxes wrap twice
+    from collections import deque
+    q = deque()
+    for _ in range(19):
+        if len(q) == 4:
+            outs.append(ctx.msm_g1_wait(q.popleft()))
+        q.append(ctx.msm_g1_sharded_submit_dev(setup, scal.data_ptr(), count))
+    while q:
+        outs.append(ctx.msm_g1_wait(q.popleft()))
+    # the same from pinned host buffers (copy on the lane's copy stream)
+    host = torch.from_numpy(synthetic.scalar_stream(0xC3, count, start=first)).pin_memory()
     for _ in range(6):
-        t = ctx.msm_g1_sharded_submit_dev(setup, scal.data_ptr(), count)
-        if prev is not None:
-            outs.append(ctx.msm_g1_wait(prev))
-        prev = t
-    outs.append(ctx.msm_g1_wait(prev))
+        if len(q) == 4:
+            outs.append(ctx.msm_g1_wait(q.popleft()))
+        q.append(ctx.msm_g1_sharded_submit(setup, host.data_ptr(), count))
+    while q:
+        outs.append(ctx.msm_g1_wait(q.popleft()))
     ret.put((rank, [o.hex() for o in outs]))
     dist.barrier()
     setup.close(); ctx.close()
