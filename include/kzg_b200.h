@@ -149,6 +149,11 @@ int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs
 int32_t kzg_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32,
                        uint64_t blobs, uint64_t n, const uint8_t* z_le32, uint8_t* y_le32,
                        uint8_t* proofs_c48);
+/* Polynomial::commit + Evaluation::generate_proof of every blob (src/polynomial.rs:200-215, 260-269) with ONE
+ * host->device pass over the coefficients: the EIP-4844-style "commit + proof" unit of BASELINE config C4. */
+int32_t kzg_commit_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32,
+                              uint64_t blobs, uint64_t n, const uint8_t* z_le32, uint8_t* commits_c48,
+                              uint8_t* y_le32, uint8_t* proofs_c48);
 
 /* ---- device-resident variants (inputs already in HBM; results still land on the host) --- */
 int32_t kzg_msm_g1_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,

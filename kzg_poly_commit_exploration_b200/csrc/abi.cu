@@ -699,6 +699,12 @@ static uint64_t batch_chunk_rows(const kzg_ctx* ctx, uint64_t blobs) {
   return (blobs >= 2 * c && blobs >= (uint64_t)ctx->opt_tree_min_rows) ? c : blobs;
 }
 
+// The first staging chunk is an eighth of the others: its copy is the only one that nothing hides (2048 rows of 4096
+// coefficients = 256 MiB, ~10 ms), and its kernels then cover the copy of the first full chunk.
+static uint64_t first_chunk_rows(uint64_t chunk, uint64_t blobs, uint64_t r0) {
+  return (r0 == 0 && blobs > chunk && chunk >= 64) ? chunk / 8 : chunk;
+}
+
 static uint64_t batch_max_trimmed(const uint8_t* coeffs, uint64_t blobs, uint64_t n) {
   uint64_t m = 0;
   for (uint64_t b = 0; b < blobs; b++) m = std::max(m, trimmed_len(coeffs + b * n * 32, n));
@@ -721,8 +727,8 @@ int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));          // scratch of earlier calls is free
   KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
   uint64_t k = 0;
-  for (uint64_t r0 = 0; r0 < blobs; r0 += chunk, k++) {
-    const uint64_t rows = std::min(chunk, blobs - r0);
+  for (uint64_t r0 = 0, rows = 0; r0 < blobs; r0 += rows, k++) {
+    rows = std::min(first_chunk_rows(chunk, blobs, r0), blobs - r0);
     uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
     if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
     KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
@@ -751,8 +757,8 @@ int32_t kzg_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_l
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));
   KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
   uint64_t k = 0;
-  for (uint64_t r0 = 0; r0 < blobs; r0 += chunk, k++) {
-    const uint64_t rows = std::min(chunk, blobs - r0);
+  for (uint64_t r0 = 0, rows = 0; r0 < blobs; r0 += rows, k++) {
+    rows = std::min(first_chunk_rows(chunk, blobs, r0), blobs - r0);
     uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
     if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
     KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
@@ -761,6 +767,46 @@ int32_t kzg_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_l
   }
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le32, yd, blobs * 32, cudaMemcpyDeviceToHost, ctx->stream));
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(proofs_c48, o, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  update_timers(ctx);
+  return KZG_OK;
+}
+
+// commit + open of every blob with ONE host->device pass over the coefficients (kzg_commit_batch followed by
+// kzg_open_batch copies them twice): chunk k+1 is staged on the copy stream while chunk k is committed and opened
+int32_t kzg_commit_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n,
+                              const uint8_t* z_le32, uint8_t* commits_c48, uint8_t* y_le32, uint8_t* proofs_c48) {
+  if (!ctx || !s || (!coeffs_le32 && blobs * n) || !z_le32 || !commits_c48 || !y_le32 || !proofs_c48) return KZG_E_BAD_ARG;
+  if (blobs == 0) return KZG_OK;
+  if (std::max<uint64_t>(n, 1) > s->n && std::max<uint64_t>(batch_max_trimmed(coeffs_le32, blobs, n), 1) > s->n)
+    return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  if (n > s->n) return fail(ctx, KZG_E_BAD_ARG, "batch with trailing-zero padding beyond the setup is not supported");
+  DeviceGuard g(ctx->device);
+  void *d, *o, *zy;
+  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(blobs * n, 1) * 32, &d));
+  KZG_TRY(scratch_get(ctx, SCR_OUT, blobs * 96, &o));
+  KZG_TRY(scratch_get(ctx, SCR_FR_A, blobs * 64, &zy));
+  uint8_t* cd = reinterpret_cast<uint8_t*>(o);
+  uint8_t* pd = cd + blobs * 48;
+  uint8_t* zd = reinterpret_cast<uint8_t*>(zy);
+  uint8_t* yd = zd + blobs * 32;
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le32, blobs * 32, cudaMemcpyHostToDevice, ctx->stream));
+  const uint64_t chunk = batch_chunk_rows(ctx, blobs);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
+  uint64_t k = 0;
+  for (uint64_t r0 = 0, rows = 0; r0 < blobs; r0 += rows, k++) {
+    rows = std::min(first_chunk_rows(chunk, blobs, r0), blobs - r0);
+    uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
+    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k % 7], 0));
+    KZG_TRY(kzg_commit_batch_dev(ctx, s, dc, rows, n, cd + r0 * 48));
+    KZG_TRY(kzg_open_batch_dev(ctx, s, dc, rows, n, zd + r0 * 32, yd + r0 * 32, pd + r0 * 48));
+  }
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(commits_c48, cd, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le32, yd, blobs * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(proofs_c48, pd, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   update_timers(ctx);
   return KZG_OK;

@@ -171,6 +171,15 @@ class Context:
         self.check(N.lib().kzg_open_batch(self._h, setup._h, _ptr(coeffs_le32), blobs, n, _ptr(z_le32), _ptr(y), _ptr(pr)))
         return (bytes(y), bytes(pr)) if y_out is None else (y, pr)
 
+    def commit_open_batch(self, setup: "Setup", coeffs_le32, blobs: int, n: int, z_le32, commits_out=None, y_out=None, proofs_out=None):
+        """commit + evaluation proof of every blob, one host->device pass over the coefficients"""
+        own = commits_out is None
+        cm = N.out(blobs * 48) if commits_out is None else commits_out
+        y = N.out(blobs * 32) if y_out is None else y_out
+        pr = N.out(blobs * 48) if proofs_out is None else proofs_out
+        self.check(N.lib().kzg_commit_open_batch(self._h, setup._h, _ptr(coeffs_le32), blobs, n, _ptr(z_le32), _ptr(cm), _ptr(y), _ptr(pr)))
+        return (bytes(cm), bytes(y), bytes(pr)) if own else (cm, y, pr)
+
     # ---- device-resident variants (addresses as ints, e.g. torch.Tensor.data_ptr()) ---------
     def msm_g1_dev(self, setup: "Setup", scalars_dev: int, n: int) -> bytes:
         o = N.out(48)

@@ -30,6 +30,8 @@ extern "C" {
     pub fn kzg_commit_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64, out_c48: *mut u8) -> i32;
     pub fn kzg_open_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64,
                           z_le32: *const u8, y_le32: *mut u8, proofs_c48: *mut u8) -> i32;
+    pub fn kzg_commit_open_batch(ctx: *mut kzg_ctx, s: *const kzg_setup, coeffs_le32: *const u8, blobs: u64, n: u64,
+                                 z_le32: *const u8, commits_c48: *mut u8, y_le32: *mut u8, proofs_c48: *mut u8) -> i32;
     // precomputed tables (once per setup) and several commitments in flight (ticket t runs on lane t mod `lanes`)
     pub fn kzg_ctx_set_option(ctx: *mut kzg_ctx, name: *const c_char, value: i64) -> i32;
     pub fn kzg_setup_prepare_msm(ctx: *mut kzg_ctx, s: *mut kzg_setup, window_bits: i32) -> i32;

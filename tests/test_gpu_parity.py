@@ -341,6 +341,8 @@ def test_blob_batch_small(ctx, c):
         assert commits[48 * b: 48 * b + 48] == O.g1_compress(O.commit_known_secret(co, S)), b
         assert int.from_bytes(ys[32 * b: 32 * b + 32], "little") == O.horner(co, z), b
         assert proofs[48 * b: 48 * b + 48] == O.g1_compress(O.proof_known_secret(co, S, z)), b
+    # the fused call (one host->device pass) returns the same three arrays
+    assert ctx.commit_open_batch(st, coeffs, blobs, n, zs) == (commits, ys, proofs)
     # single commits below the table size take the same fixed-base path
     co = util.to_ints(coeffs[: 100 * 32])
     assert ctx.commit(st, coeffs[: 100 * 32]) == O.g1_compress(O.commit_known_secret(co, S))
@@ -583,6 +585,7 @@ def test_config_c4_batch_default_path(ctx):
     try:
         commits = ctx.commit_batch(st, coeffs, blobs, n)
         ys, proofs = ctx.open_batch(st, coeffs, blobs, n, zs)
+        assert ctx.commit_open_batch(st, coeffs, blobs, n, zs) == (commits, ys, proofs)   # fused, chunked staging
     finally:
         ctx.set_option("tree_chunk_rows", 2048)
     for b in (0, 1, 399, 400, 401, 799, 800, blobs - 1):
