@@ -473,8 +473,8 @@ def blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, blobs_total, 
     torch.cuda.synchronize()
 
     def step_dev():
-        ctx.commit_batch_dev(setup, coeffs.data_ptr(), count, n, commits.data_ptr())
-        ctx.open_batch_dev(setup, coeffs.data_ptr(), count, n, zs.data_ptr(), ys.data_ptr(), proofs.data_ptr())
+        # kzg_commit_open_batch_dev: the commitments on one lane of the context, the proofs on another
+        ctx.commit_open_batch_dev(setup, coeffs.data_ptr(), count, n, zs.data_ptr(), commits.data_ptr(), ys.data_ptr(), proofs.data_ptr())
         ctx.sync()
 
     def step_e2e():

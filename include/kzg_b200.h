@@ -188,6 +188,10 @@ int32_t kzg_commit_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeff
 int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev,
                            uint64_t blobs, uint64_t n, const void* z_dev, void* y_dev,
                            void* proofs_c48_dev);
+/* commit + open of the same rows, the two MSM batches on two lanes of the context (inputs ready on the engine stream) */
+int32_t kzg_commit_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev,
+                                  uint64_t blobs, uint64_t n, const void* z_dev, void* commits_c48_dev,
+                                  void* y_dev, void* proofs_c48_dev);
 int32_t kzg_evaluate_dev(kzg_ctx* ctx, const void* coeffs_dev, uint64_t n, const uint8_t z_le[32],
                          uint8_t y_le[32]);
 

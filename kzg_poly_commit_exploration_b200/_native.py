@@ -52,6 +52,7 @@ SIGNATURES = {
     "kzg_msm_g1": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "kzg_commit_batch": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp]),
     "kzg_open_batch": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "kzg_commit_open_batch_dev": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "kzg_commit_open_batch": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "kzg_msm_g1_dev": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "kzg_msm_g1_submit": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(_i32)]),

@@ -644,6 +644,18 @@ int32_t kzg_open(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, u
 }
 
 // ---- blob batches ------------------------------------------------------------------------------------
+// lane l >= 1 of a context (hidden sibling context: own streams and scratch), created on first use
+static int32_t sibling_lane(kzg_ctx* ctx, int l, kzg_ctx** lane) {
+  if (l < 1 || l >= KZG_MAX_LANES) return KZG_E_BAD_ARG;
+  if (!ctx->lane[l]) {
+    int32_t st = kzg_ctx_create(&ctx->lane[l], ctx->device);
+    if (st != KZG_OK) return fail(ctx, st, "could not create another lane of the context");
+  }
+  copy_options(ctx->lane[l], ctx);
+  *lane = ctx->lane[l];
+  return KZG_OK;
+}
+
 static int32_t batch_points_out(kzg_ctx* ctx, const G1Xyzz* pts, uint64_t blobs, uint8_t* out_c48_dev) {
   void* aff;
   KZG_TRY(scratch_get(ctx, SCR_BATCH_AFF, blobs * sizeof(G1Affine), &aff));
@@ -690,6 +702,31 @@ int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_
   KZG_TRY(msm_batch_any(ctx, s, reinterpret_cast<uint8_t*>(q), blobs, nq, n, reinterpret_cast<G1Xyzz*>(pts)));
   KZG_TRY(batch_points_out(ctx, reinterpret_cast<G1Xyzz*>(pts), blobs, reinterpret_cast<uint8_t*>(proofs_c48_dev)));
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  return KZG_OK;
+}
+
+// commit + open of the same rows: two independent MSM batches, the commitments on the context's own lane and the
+// proofs (quotient scan + MSM) on a sibling lane, so that the latency-bound inversion chains of one tree (3 small
+// launches per round, ~9 % of a batch) run under the bulk kernels of the other.  Inputs must be ready on ctx->stream;
+// on return ctx->stream has joined the sibling lane.
+int32_t kzg_commit_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n,
+                                  const void* z_dev, void* commits_c48_dev, void* y_dev, void* proofs_c48_dev) {
+  if (!ctx || !s || (!coeffs_dev && blobs * n) || !z_dev || !commits_c48_dev || !y_dev || !proofs_c48_dev) return KZG_E_BAD_ARG;
+  if (blobs == 0) return KZG_OK;
+  DeviceGuard g(ctx->device);
+  kzg_ctx* side = ctx;
+  if (ctx->opt_lanes > 1) KZG_TRY(sibling_lane(ctx, 1, &side));
+  if (side != ctx) {
+    KZG_CUDA_OK(ctx, cudaEventRecord(side->ev_copy[0], ctx->stream));          // inputs (and earlier users of the outputs) done
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(side->stream, side->ev_copy[0], 0));
+  }
+  int32_t st = kzg_open_batch_dev(side, s, coeffs_dev, blobs, n, z_dev, y_dev, proofs_c48_dev);
+  if (st != KZG_OK) { if (side != ctx) ctx->err = side->err; return st; }
+  KZG_TRY(kzg_commit_batch_dev(ctx, s, coeffs_dev, blobs, n, commits_c48_dev));
+  if (side != ctx) {
+    KZG_CUDA_OK(ctx, cudaEventRecord(side->ev_copy[1], side->stream));
+    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, side->ev_copy[1], 0));
+  }
   return KZG_OK;
 }
 
@@ -801,8 +838,7 @@ int32_t kzg_commit_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* c
     if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
     KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
     KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k % 7], 0));
-    KZG_TRY(kzg_commit_batch_dev(ctx, s, dc, rows, n, cd + r0 * 48));
-    KZG_TRY(kzg_open_batch_dev(ctx, s, dc, rows, n, zd + r0 * 32, yd + r0 * 32, pd + r0 * 48));
+    KZG_TRY(kzg_commit_open_batch_dev(ctx, s, dc, rows, n, zd + r0 * 32, cd + r0 * 48, yd + r0 * 32, pd + r0 * 48));
   }
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(commits_c48, cd, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
   KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le32, yd, blobs * 32, cudaMemcpyDeviceToHost, ctx->stream));

@@ -215,6 +215,10 @@ class Context:
     def open_batch_dev(self, setup: "Setup", coeffs_dev: int, blobs: int, n: int, z_dev: int, y_dev: int, proofs_dev: int):
         self.check(N.lib().kzg_open_batch_dev(self._h, setup._h, _ptr(coeffs_dev), blobs, n, _ptr(z_dev), _ptr(y_dev), _ptr(proofs_dev)))
 
+    def commit_open_batch_dev(self, setup: "Setup", coeffs_dev: int, blobs: int, n: int, z_dev: int, commits_dev: int, y_dev: int, proofs_dev: int):
+        self.check(N.lib().kzg_commit_open_batch_dev(self._h, setup._h, _ptr(coeffs_dev), blobs, n, _ptr(z_dev), _ptr(commits_dev),
+                                                     _ptr(y_dev), _ptr(proofs_dev)))
+
     def evaluate_dev(self, coeffs_dev: int, n: int, z_le: bytes) -> bytes:
         o = N.out(32)
         self.check(N.lib().kzg_evaluate_dev(self._h, _ptr(coeffs_dev), n, _ptr(z_le), o))
