@@ -212,6 +212,7 @@ int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "tree_min_rows") ctx->opt_tree_min_rows = (int)value;
   else if (n == "tree_chunk_rows") ctx->opt_tree_chunk_rows = (int)value;
   else if (n == "tree_min_pairs") ctx->opt_tree_min_pairs = value;
+  else if (n == "setup_tree_min") ctx->opt_setup_tree_min = (int)value;
   else if (n == "lanes") {
     if (ctx->lanes_in_use) return fail(ctx, KZG_E_BAD_ARG, "the number of lanes is fixed once a call has been submitted");
     ctx->opt_lanes = (int)std::min<int64_t>(KZG_MAX_LANES, std::max<int64_t>(1, value));
@@ -405,7 +406,7 @@ static void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
   dst->opt_tree_min_rows = src->opt_tree_min_rows; dst->opt_tree_chunk_rows = src->opt_tree_chunk_rows;
   dst->opt_tree_min_pairs = src->opt_tree_min_pairs; dst->opt_inv_top_fan = src->opt_inv_top_fan; dst->opt_inv_top = src->opt_inv_top;
   dst->opt_msm_tree_rounds = src->opt_msm_tree_rounds; dst->opt_acc_min_entries = src->opt_acc_min_entries;
-  dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_acc_minblocks = src->opt_acc_minblocks;
+  dst->opt_setup_tree_min = src->opt_setup_tree_min; dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_acc_minblocks = src->opt_acc_minblocks;
 }
 
 static int32_t lane_of(kzg_ctx* ctx, uint32_t ticket, kzg_ctx** lane) {

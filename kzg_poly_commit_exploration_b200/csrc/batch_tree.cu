@@ -352,4 +352,56 @@ int32_t msm_fixed_batch_tree(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* sc
   return KZG_OK;
 }
 
+// ---- N fixed-base multiplications of ONE base (powers-of-tau generation, setup.cu) ------------------------------------
+// out[i] = k_i * B with tab[(j << (c-1)) + d-1] = d * 2^(c j) * B: every output is the sum of W table points, which is
+// exactly a "row" of one coefficient for the kernels above (n = 1, stride = 1, base index 0).  Round 1 pairs the W
+// lookups, log2(W/2) generic rounds finish the sum, and the last round writes the AFFINE result straight into `out`:
+// 15 additions x 6 products = 90 Fq products per point and no per-point inversion, against 16 mixed additions x 10 +
+// the batched to-affine (~165) on the XYZZ path (k_setup_points).
+int32_t fixed_base_points_tree(kzg_ctx* ctx, const G1Affine* tab, int c, int W, const uint8_t* scalars_dev, uint64_t N,
+                               G1Affine* out_dev) {
+  if (N == 0) return KZG_OK;
+  if (W > 32 || W < 3) return fail(ctx, KZG_E_BAD_ARG, "tree path needs 3..32 windows");
+  const uint64_t KP = (uint64_t)(W + 1) / 2;
+  const uint64_t chunk = 1ull << 22;   // rows per pass: each of the 4 rounds pays one ~0.2 ms inversion chain (6.5 GB of scratch)
+  const uint64_t top = (uint64_t)ctx->opt_inv_top;
+  const uint64_t rows_max = N < chunk ? N : chunk;
+  const uint64_t pts1 = rows_max * KP;
+  void *A, *B, *PF, *TW;
+  KZG_TRY(scratch_get(ctx, SCR_TREE_A, pts1 * sizeof(G1Affine), &A));
+  KZG_TRY(scratch_get(ctx, SCR_TREE_B, (pts1 / 2 + rows_max + 16) * sizeof(G1Affine), &B));
+  KZG_TRY(scratch_get(ctx, SCR_TREE_PREFIX, pts1 * sizeof(Fq), &PF));
+  const uint64_t Tmax = rows_max + 16;
+  KZG_TRY(scratch_get(ctx, SCR_TREE_TOT, (Tmax + invert_scratch_elems(Tmax, top)) * sizeof(Fq), &TW));
+  Fq* prefix = reinterpret_cast<Fq*>(PF);
+  Fq* tot = reinterpret_cast<Fq*>(TW);
+  Fq* inv_ws = tot + Tmax;
+  for (uint64_t r0 = 0; r0 < N; r0 += chunk) {
+    const uint64_t rows = N - r0 < chunk ? N - r0 : chunk;
+    const uint8_t* sc = scalars_dev + r0 * 32;
+    k_r1_den<<<blocks_for(rows, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, 1, 1, tab, c, W, prefix, tot);
+    KZG_LAUNCHED(ctx);
+    KZG_TRY(batch_invert_inplace(ctx, tot, rows, inv_ws, top));
+    G1Affine* cur = reinterpret_cast<G1Affine*>(A);
+    G1Affine* nxt = reinterpret_cast<G1Affine*>(B);
+    k_r1_add<<<blocks_for(rows, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, 1, 1, tab, c, W, prefix, tot, cur);
+    KZG_LAUNCHED(ctx);
+    uint64_t L = KP;
+    while (L > 1) {
+      const uint64_t Lout = (L + 1) / 2;
+      const uint64_t NP = rows * Lout;
+      const uint64_t Tn = (NP + TR_K - 1) / TR_K;
+      G1Affine* dst = Lout == 1 ? out_dev + r0 : nxt;
+      k_rn_den<<<blocks_for(Tn, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(cur, rows, L, Lout, Tn, prefix, tot);
+      KZG_LAUNCHED(ctx);
+      KZG_TRY(batch_invert_inplace(ctx, tot, Tn, inv_ws, top));
+      k_rn_add<<<blocks_for(Tn, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(cur, rows, L, Lout, Tn, prefix, tot, dst);
+      KZG_LAUNCHED(ctx);
+      nxt = cur; cur = dst;
+      L = Lout;
+    }
+  }
+  return KZG_OK;
+}
+
 }  // namespace kzg

@@ -71,6 +71,7 @@ struct kzg_ctx {
     bool busy = false;
   } pending[kzg::KZG_MAX_LANES];
   uint32_t next_ticket = 0;
+  int opt_setup_tree_min = 1 << 18;    // setup generation: affine-tree path from this many points on (0 = never)
   int opt_lanes = 4;                   // calls in flight (1 .. KZG_MAX_LANES); fixed once the first ticket is out
   int lanes_in_use = 0;                // opt_lanes latched by the first submit
   kzg_ctx* lane[kzg::KZG_MAX_LANES] = {};   // ticket t runs on lane t mod L; lane 0 is the context itself, the others are hidden
@@ -196,6 +197,9 @@ int32_t msm_fixed_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars
 // same contract as msm_fixed_batch; affine pairwise tree with grid-wide shared inversions (large batches)
 int32_t msm_fixed_batch_tree(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t rows,
                              uint64_t n, uint64_t stride_scalars, G1Xyzz* out_dev);
+// N fixed-base multiplications of one base through the same affine trees; affine results (setup generation)
+int32_t fixed_base_points_tree(kzg_ctx* ctx, const G1Affine* tab, int c, int W, const uint8_t* scalars_dev, uint64_t N,
+                               G1Affine* out_dev);
 
 // grid-wide batch inversion: v[i] <- 1 / v[i], i < N, no zeros; ws holds invert_scratch_elems(N, top) Fq
 size_t invert_scratch_elems(uint64_t N, uint64_t top);

@@ -307,11 +307,15 @@ int32_t setup_generate_dev(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t f
   Fr raw, s_mont; fr_load_le(raw, le); to_mont(s_mont, raw);
   void* pw; void* xy;
   KZG_TRY(scratch_get(ctx, SCR_FR_A, n * sizeof(Fr), &pw));
-  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, n * sizeof(G1Xyzz), &xy));
   const uint32_t K = 32;
   uint64_t threads = (n + K - 1) / K;
   k_powers<<<blocks_for(threads, 128), 128, 0, ctx->stream>>>(s_mont, first, n, K, reinterpret_cast<Fr*>(pw));
   KZG_LAUNCHED(ctx);
+  // large ranges: the 16 table points of every item are summed by affine pairwise trees with shared inversions
+  // (batch_tree.cu, 90 Fq products per point); small ranges: one XYZZ walk per thread + batched to-affine (~165)
+  if (ctx->opt_setup_tree_min > 0 && n >= (uint64_t)ctx->opt_setup_tree_min)
+    return fixed_base_points_tree(ctx, ctx->gtable, GT_C, GT_W, reinterpret_cast<const uint8_t*>(pw), n, bases_dev);
+  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, n * sizeof(G1Xyzz), &xy));
   k_setup_points<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(reinterpret_cast<Fr*>(pw), n, ctx->gtable,
                                                               reinterpret_cast<G1Xyzz*>(xy));
   KZG_LAUNCHED(ctx);

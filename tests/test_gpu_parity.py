@@ -64,6 +64,26 @@ def test_setup_shard_offset_and_secret_reduction(ctx):
     st.close()
 
 
+@pytest.mark.parametrize("secret_int", [0, 1, 2, O.R - 1, int.from_bytes(SECRET, "big")])
+def test_setup_affine_tree_path(secret_int):
+    """setup generation through the affine pairwise trees (fixed_base_points_tree, the path of large ranges) forced on
+    a small range: same bytes as the XYZZ walk, including the degenerate secrets (s = 0: all infinity after item 0,
+    s = 1: every item G, s = r - 1: G and -G alternate, s = 2: tiny scalars with mostly-zero digits)."""
+    import kzg_poly_commit_exploration_b200 as pkg
+    c2 = pkg.Context(0)
+    secret = secret_int.to_bytes(32, "big")
+    n, first = 531, 7
+    c2.set_option("setup_tree_min", 0)
+    ref = c2.setup_generate(secret, n, first=first)
+    c2.set_option("setup_tree_min", 1)
+    st = c2.setup_generate(secret, n, first=first)
+    a, b = ref.export_g1(), st.export_g1()
+    assert a == b
+    for i in [0, 1, 2, 100, n - 1]:
+        assert b[48 * i: 48 * i + 48] == g1c(pow(secret_int % O.R, first + i, O.R)), i
+    ref.close(); st.close(); c2.close()
+
+
 @pytest.mark.parametrize("secret_int", [0, 1])
 def test_setup_degenerate_secrets(ctx, secret_int):
     # s = 0: item 0 is the generator, every later item is infinity (SURVEY §8c edge 7); s = 1: all G
