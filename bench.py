@@ -360,7 +360,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": _clocks_summary(samples),
             "roofline": {
-                "bound": "int32-multiply (IMAD.WIDE), not hbm/tensor: MSM is integer-compute-bound",
+                "bound": "int32-multiply",
+                "bound_note": "integer-multiply pipe (IMAD.WIDE), neither hbm nor tensor: the MSM is integer-compute-bound "
+                              "(north_star); the HBM side of the dominant kernel is reported under dominant_kernel.hbm",
                 "kernel": (f"bucket accumulation = k_seg_den + batch inversion + k_seg_add ({rounds} affine halving rounds, "
                            "msm_tree.cu) + k_bucket_acc" if tree else "k_bucket_acc"),
                 "achieved": phase_achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-MAC/s",
@@ -433,6 +435,8 @@ def other_configs(ctx, synthetic, torch, dist, dev, world, rank):
     st.close()
     out["setup_2^22_g1"] = {"metric": "setup_points_per_s", "value": n5 / dt, "unit": "G1 points/s", "ms": dt * 1e3,
                             "sharding": f"index range, {per} points/GPU", "wide_mac_per_point": 48000,
+                            "path": "affine pairwise trees over the generator table (fixed_base_points_tree), 90 Fq products per point"
+                                    if per >= (1 << 18) else "XYZZ table walk + batched to-affine",
                             "g2_points_per_s_per_gpu": (1 << 16) / dt_g2}
     if world == 1:
         n2 = (1 << 16) + 1
@@ -513,13 +517,14 @@ def blob_batch(ctx, pkg, synthetic, torch, dist, dev, world, rank, blobs_total, 
             "config": {"workload": f"{blobs_total} blobs x {n} coefficients (BASELINE config C4), commit + proof, sharded by blob",
                        "fixed_base_window_bits": fixed_window, "lookups_per_coefficient": W,
                        "table_gib": round(n * W * (1 << (fixed_window - 1)) * 96 / 2**30, 2), "table_build_s": round(table_s, 2)},
-            "dev_equals_e2e": bool(same), "scaling": "weak" if world > 1 else "n/a"}
+            "dev_equals_e2e": bool(same),
+            "scaling": f"strong ({blobs_total} blobs in total, {count} per GPU, no data-path collective)" if world > 1 else "n/a"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--window", type=int, default=int(os.environ.get("KZG_WINDOW", "0")))
