@@ -42,7 +42,7 @@ struct kzg_ctx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   kzg::G1Affine* gtable = nullptr;     // [16][32768] multiples of the generator (setup generation)
-  void* g2table = nullptr;             // [32][255] multiples of the G2 generator (setup_g2.cu)
+  void* g2table = nullptr;             // [20][4096] signed-window multiples of the G2 generator (setup_g2.cu)
   int opt_msm_window = 0;              // 0 = auto
   int opt_fixed_window = 0;            // 0 = auto
   int opt_reduce_chunk = 16;

@@ -287,6 +287,27 @@ def test_setup_g2_degenerate_secrets(ctx, secret_int):
     st.close()
 
 
+@pytest.mark.parametrize("secret_int", [0, 1, 2, O.R - 1, int.from_bytes(SECRET, "big")])
+def test_setup_g2_affine_tree_path(secret_int):
+    """[s^i]G2 through the affine pairwise trees over Fq2 (the path of ranges >= 2^16 items) forced on a small range:
+    same bytes as the XYZZ walk and as the oracle, including the degenerate secrets (infinity operands, P + P, P - P)."""
+    import kzg_poly_commit_exploration_b200 as pkg
+    c2 = pkg.Context(0)
+    sec = secret_int.to_bytes(32, "big")
+    n, first = 77, 3
+    out = []
+    for tree_min in (0, 1):
+        c2.set_option("setup_tree_min", tree_min)
+        st = c2.setup_generate(sec, n, first=first)
+        st.generate_g2(sec, n)
+        out.append(st.export_g2())
+        st.close()
+    assert out[0] == out[1]
+    for i in (0, 1, 2, 40, n - 1):
+        assert out[1][96 * i: 96 * i + 96] == O.g2_compress(O.g2_from_scalar(pow(secret_int % O.R, first + i, O.R))), i
+    c2.close()
+
+
 # ---- adversarial scalar sets (bucket collisions, heavy buckets, cancellations) ----------------------
 @pytest.mark.parametrize("kind", ["zeros", "ones", "equal", "rminus1", "small", "alternating"])
 def test_commit_adversarial_scalars(ctx, setup8k, kind):
