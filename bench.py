@@ -39,6 +39,37 @@ TRAFFIC_NCU = 2.707788288e9 + 0.814427904e9
 
 
 def _clock_sampler(stop, samples, device_index):
+    """SM clock / throttle reasons DURING the timed region.  In-process NVML (nvidia_ml_py) when it loads: a sample
+    costs microseconds, where spawning nvidia-smi costs ~0.4 s and yields 2-4 samples per run; nvidia-smi otherwise."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(device_index)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:                                   # NVML enumerates physical devices
+            try:
+                h = nv.nvmlDeviceGetHandleByIndex(int(vis.split(",")[device_index]))
+            except Exception:
+                pass
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = get_reasons(h)
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            samples.append([str(sm), str(mx), str(pw), hex(r)] +
+                           ["Active" if r & bits[k] else "Not Active" for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            stop.wait(0.01)
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
@@ -430,7 +461,7 @@ def other_configs(ctx, synthetic, torch, dist, dev, world, rank):
     dt = sorted(dts)[1]                       # median of 3
     t0 = time.perf_counter()
     n_g2 = min(per, 1 << 18)
-    st.generate_g2(synthetic.BENCH_SECRET_BE, 2)            # builds the G2 generator table (once per ctx)
+    st.generate_g2(synthetic.BENCH_SECRET_BE, n_g2)         # builds the G2 generator table (once per ctx) and the scratch
     ctx.sync()
     t0 = time.perf_counter()
     st.generate_g2(synthetic.BENCH_SECRET_BE, n_g2)
