@@ -217,7 +217,7 @@ def run_ours(args):
             scal_dev.copy_(host, non_blocking=True)
         return step_dev()
 
-    def two_in_flight(k, submit):
+    def calls_in_flight(k, submit):
         # submit / wait with `lanes` calls in flight (ticket t runs on lane t mod lanes of the context): every step is a
         # complete MSM whose 48-byte result is read back; the copy and the bulk kernels of one step overlap the
         # latency-bound phases (inversion chains, bucket reduction) of the others
@@ -235,13 +235,13 @@ def run_ours(args):
 
     def steps_dev_pipelined(k):
         if world == 1:
-            return two_in_flight(k, lambda: ctx.msm_g1_submit_dev(setup, scal_dev.data_ptr(), per))
-        return two_in_flight(k, lambda: ctx.msm_g1_sharded_submit_dev(setup, scal_dev.data_ptr(), per))
+            return calls_in_flight(k, lambda: ctx.msm_g1_submit_dev(setup, scal_dev.data_ptr(), per))
+        return calls_in_flight(k, lambda: ctx.msm_g1_sharded_submit_dev(setup, scal_dev.data_ptr(), per))
 
     def steps_e2e_pipelined(k):
         if world == 1:
-            return two_in_flight(k, lambda: ctx.msm_g1_submit(setup, host.data_ptr(), per))
-        return two_in_flight(k, lambda: ctx.msm_g1_sharded_submit(setup, host.data_ptr(), per))
+            return calls_in_flight(k, lambda: ctx.msm_g1_submit(setup, host.data_ptr(), per))
+        return calls_in_flight(k, lambda: ctx.msm_g1_sharded_submit(setup, host.data_ptr(), per))
 
     wall_ms = [0.0]     # host clock of the last timed region (max over ranks), reported beside the device time
 
