@@ -33,12 +33,17 @@ for lanes in lanes_list:
     ctx.msm_g1_dev(st, dev.data_ptr(), n); ctx.sync()
     single = ctx.last_kernel_ms(1)
 
+    host_s = [0.0]
+
     def run(k, submit):
+        import time
         q = deque()
         for _ in range(k):
             if len(q) == lanes:
                 assert ctx.msm_g1_wait(q.popleft()) == ref
+            t0 = time.perf_counter()
             q.append(submit())
+            host_s[0] += time.perf_counter() - t0
         while q:
             assert ctx.msm_g1_wait(q.popleft()) == ref
 
@@ -47,9 +52,10 @@ for lanes in lanes_list:
                          ("e2e", lambda: ctx.msm_g1_submit(st, host.data_ptr(), n))):
         run(2 * lanes + 2, submit)
         ctx.sync(); ctx.timer_start()
+        host_s[0] = 0.0
         run(steps, submit)
         ms = ctx.timer_stop() / steps
-        res.append(f"{name} {ms:.3f} ms ({n / ms / 1e3:.1f} M points/s)")
+        res.append(f"{name} {ms:.3f} ms ({n / ms / 1e3:.1f} M points/s, host {host_s[0] / steps * 1e3:.3f} ms in submit)")
     print(f"n=2^{logn} c={window or 'auto'} {' '.join(rest)} lanes={lanes}: one call {single:.3f} ms  " + "  ".join(res) + f"  ok={ok}", flush=True)
     del host, dev
     st.close(); ctx.close()
