@@ -307,19 +307,36 @@ int32_t kzg_setup_import_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t* g2_c96, u
   if (!ctx || !s || (!g2_c96 && count)) return KZG_E_BAD_ARG;
   if (count > s->n) return fail(ctx, KZG_E_BAD_ARG, "more G2 items than setup items");
   // Deserialize for G2Point (src/curves.rs:273-343): length fixed by the ABI, blst_p2_uncompress semantics
-  // (flags, coordinates < q, on-curve; no subgroup check) — validated on the host, point by point
-  for (uint64_t i = 0; i < count; i++) {
-    if (kzg_g2_check(g2_c96 + 96 * i) != KZG_OK) {
-      ctx->err = "Got error while uncompressing: G2 point " + std::to_string(i);
-      return KZG_E_BAD_POINT;
-    }
-  }
+  // (flags, coordinates < q, Fq2 square root, on-curve; no subgroup check).  A handful of points (the CLI's setup.json)
+  // is validated on the host; larger sets on the device, one thread per point (a host square root costs ~0.1 ms).
   DeviceGuard g(ctx->device);
-  KZG_TRY(setup_g2_alloc(ctx, s, count));
-  if (count) {
-    KZG_CUDA_OK(ctx, cudaMemcpyAsync(s->g2_c96, g2_c96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
-    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  const bool on_device = count >= 64;
+  if (!on_device) {
+    for (uint64_t i = 0; i < count; i++) {
+      if (kzg_g2_check(g2_c96 + 96 * i) != KZG_OK) {
+        ctx->err = "Got error while uncompressing: G2 point " + std::to_string(i);
+        return KZG_E_BAD_POINT;
+      }
+    }
+    KZG_TRY(setup_g2_alloc(ctx, s, count));
+    if (count) {
+      KZG_CUDA_OK(ctx, cudaMemcpyAsync(s->g2_c96, g2_c96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+      KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return KZG_OK;
   }
+  void* stage;                                   // validated in scratch first: a rejected import leaves the setup untouched
+  KZG_TRY(scratch_get(ctx, SCR_OUT, count * 96, &stage));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(stage, g2_c96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+  int64_t bad = -1;
+  KZG_TRY(validate_g2_points(ctx, reinterpret_cast<const uint8_t*>(stage), count, &bad));
+  if (bad >= 0) {
+    ctx->err = "Got error while uncompressing: G2 point " + std::to_string(bad);
+    return KZG_E_BAD_POINT;
+  }
+  KZG_TRY(setup_g2_alloc(ctx, s, count));
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(s->g2_c96, stage, count * 96, cudaMemcpyDeviceToDevice, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return KZG_OK;
 }
 

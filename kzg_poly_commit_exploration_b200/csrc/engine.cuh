@@ -166,6 +166,8 @@ int32_t build_fixed_table(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int c);
 // [s^(first+i)]G2, i < n, as 96-byte compressed points (device)
 int32_t setup_generate_g2_dev(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t first, uint64_t n,
                               uint8_t* out_c96_dev);
+// on-curve / encoding check of n compressed G2 points (device); bad_index = first malformed point or -1
+int32_t validate_g2_points(kzg_ctx* ctx, const uint8_t* in_c96_dev, uint64_t n, int64_t* bad_index);
 
 // ---- msm.cu (K2) -----------------------------------------------------------------------------
 // result_dev: one G1Xyzz (device).  Uses s->msm_tab (built on demand).

@@ -272,7 +272,26 @@ def test_setup_g2_kat_and_known_secret(ctx):
     with pytest.raises(Exception) as ei:
         imp.import_g2(bytes(bad))
     assert "uncompress" in str(ei.value)
-    for h in (st, sh, imp):
+    # larger sets are validated on the device (k_g2_validate): round trip, and the FIRST malformed point is reported
+    big = ctx.setup_import_g1(st.export_g1())
+    big.import_g2(g2)
+    assert big.export_g2() == g2
+    bad = bytearray(g2); bad[96 * 137] &= 0x7F; bad[96 * 250] |= 0x40        # 137: compression flag cleared; 250: infinity flag on a finite x
+    with pytest.raises(Exception) as ei:
+        big.import_g2(bytes(bad))
+    assert "G2 point 137" in str(ei.value)
+    # an x that is not on the twist: found with the library's own host-side check (same uncompress code, host build)
+    import ctypes as C
+    L = native_lib()
+    off = bytearray(g2[96 * 5: 96 * 6])
+    while L.kzg_g2_check((C.c_uint8 * 96).from_buffer_copy(bytes(off))) == 0:
+        off[95] = (off[95] + 1) & 0xFF
+    bad = bytearray(g2); bad[96 * 201: 96 * 202] = off
+    with pytest.raises(Exception) as ei:
+        big.import_g2(bytes(bad))
+    assert "G2 point 201" in str(ei.value)
+    assert big.export_g2() == g2                                             # a rejected import leaves the setup untouched
+    for h in (st, sh, imp, big):
         h.close()
 
 
