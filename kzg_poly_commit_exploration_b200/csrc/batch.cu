@@ -27,14 +27,6 @@ __device__ __forceinline__ void ld_affine_b(G1Affine& o, const G1Affine* p) {
   }
 }
 
-__device__ __forceinline__ uint32_t window_fb(const uint32_t* k, int bit, int c) {
-  int w = bit >> 5, sh = bit & 31;
-  if (w >= 8) return 0;
-  uint64_t lo = k[w];
-  if (w + 1 < 8) lo |= (uint64_t)k[w + 1] << 32;
-  return (uint32_t)(lo >> sh) & ((1u << c) - 1u);
-}
-
 __global__ void __launch_bounds__(FB_THREADS)
 k_fixed_batch(const uint8_t* __restrict__ scalars, uint64_t n, uint64_t stride, const G1Affine* __restrict__ fix,
               int c, int W, uint32_t splits, G1Xyzz* __restrict__ out) {
@@ -53,17 +45,15 @@ k_fixed_batch(const uint8_t* __restrict__ scalars, uint64_t n, uint64_t stride, 
       k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
     }
     fr_canon_reduce(k);
-    const bool flip = fr_fold_half(k);
-    uint32_t carry = 0;
+    SignedDigits sd; sd.init(k, c);
     const G1Affine* row = fix + (((size_t)i * W) << (c - 1));
 #pragma unroll 1
     for (int j = 0; j < W; j++) {
-      uint32_t d = window_fb(k.v, j * c, c) + carry;
-      bool negd = d > half;
-      if (negd) { d = (1u << c) - d; carry = 1; } else carry = 0;
+      bool neg;
+      const uint32_t d = sd.next(j, &neg);
       if (d != 0) {
         G1Affine p; ld_affine_b(p, row + ((size_t)j << (c - 1)) + (d - 1));
-        madd(acc, p, negd != flip);
+        madd(acc, p, neg);
       }
     }
   }

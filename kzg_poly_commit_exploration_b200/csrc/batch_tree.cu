@@ -24,14 +24,6 @@ constexpr int TR_THREADS = 128;
 constexpr int INV_FAN = 8;         // fan-in of the batch-inversion product tree
 
 // ---- round 1: the W table lookups of one coefficient, paired (2m, 2m+1) -----------------------------------
-__device__ __forceinline__ uint32_t window_tr(const uint32_t* k, int bit, int c) {
-  int w = bit >> 5, sh = bit & 31;
-  if (w >= 8) return 0;
-  uint64_t lo = k[w];
-  if (w + 1 < 8) lo |= (uint64_t)k[w + 1] << 32;
-  return (uint32_t)(lo >> sh) & ((1u << c) - 1u);
-}
-
 // signed digits of the scalar of (row, i): dig[j] = |d_j| | sign << 31
 __device__ __forceinline__ void digits_of(const uint8_t* scalars, uint64_t row, uint64_t i, uint64_t stride, int c, int W,
                                           uint32_t* dig) {
@@ -41,14 +33,11 @@ __device__ __forceinline__ void digits_of(const uint8_t* scalars, uint64_t row, 
   k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w;
   k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
   fr_canon_reduce(k);
-  const bool flip = fr_fold_half(k);
-  const uint32_t half = 1u << (c - 1);
-  uint32_t carry = 0;
+  SignedDigits sd; sd.init(k, c);
   for (int j = 0; j < W; j++) {
-    uint32_t d = window_tr(k.v, j * c, c) + carry;
-    bool negd = d > half;
-    if (negd) { d = (1u << c) - d; carry = 1; } else carry = 0;
-    dig[j] = d | ((negd != flip) ? 0x80000000u : 0u);
+    bool neg;
+    const uint32_t d = sd.next(j, &neg);
+    dig[j] = d | (neg ? 0x80000000u : 0u);
   }
 }
 

@@ -7,6 +7,7 @@
 #include <vector>
 #include "../../include/kzg_b200.h"
 #include "g1.cuh"
+#include "recode.cuh"
 
 namespace kzg {
 
@@ -139,11 +140,7 @@ constexpr uint32_t MSM_TAB_PITCH = 128;
 constexpr uint32_t DENSE_PITCH = 96;   // sizeof(G1Affine): the dense point arrays between the halving rounds
 
 // ---- window geometry ------------------------------------------------------------------
-inline int windows_for(int c) { return (255 + c - 1) / c; }
-// The recoders first fold the scalar into [0, (r-1)/2] (fr_fold_half: k -> r - k with every digit's sign flipped), so
-// k < 2^254.  Signed-digit recoding needs the top window to absorb a carry: with W = ceil(255/c) windows the top
-// window holds at most 254 - c*(W-1) <= c - 1 bits, so digit + carry <= 2^(c-1) and the carry never leaves it
-// (SURVEY A.2 with one bit less).  c = 17 needs 15 windows, c = 15 needs 17, c = 16 still 16.
+// window geometry and signed-digit recoding of folded scalars: recode.cuh (windows_for, SignedDigits)
 int auto_msm_window(uint64_t n);
 int auto_tree_rounds(uint64_t entries);   // msm.cu: affine halving rounds for W*n bucket entries
 

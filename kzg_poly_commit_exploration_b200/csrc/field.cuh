@@ -240,7 +240,7 @@ KZG_HD void fr_canon_reduce(Fr& a) {
 
 // Halve the range of a canonical scalar before the signed-digit recoding: for k > (r-1)/2 continue with r - k and
 // flip the sign of every digit ([k]P = -[r-k]P).  Afterwards k < 2^254, so ceil(255/c) windows of c bits hold it
-// together with the top carry (windows_for, engine.cuh) - one window fewer when c divides 255 (c = 15, 17).
+// together with the top carry (windows_for, recode.cuh) - one window fewer when c divides 255 (c = 15, 17).
 // Returns true when the scalar was replaced by r - k.
 KZG_HD bool fr_fold_half(Fr& k) {
   uint32_t t[8]; uint32_t br = 0;

@@ -38,14 +38,6 @@ __device__ __forceinline__ void ld_scalar(Fr& o, const uint8_t* p) {
   o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
 }
 
-__device__ __forceinline__ uint32_t window_at(const uint32_t* k, int bit, int c) {
-  int w = bit >> 5, sh = bit & 31;
-  if (w >= 8) return 0;
-  uint64_t lo = k[w];
-  if (w + 1 < 8) lo |= (uint64_t)k[w + 1] << 32;
-  return (uint32_t)(lo >> sh) & ((1u << c) - 1u);
-}
-
 // ---- 1. recode -------------------------------------------------------------------------------
 __global__ void k_recode(const uint8_t* __restrict__ scalars, uint64_t n, int c, int W, uint64_t n_stride,
                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
@@ -53,15 +45,13 @@ __global__ void k_recode(const uint8_t* __restrict__ scalars, uint64_t n, int c,
   if (i >= n) return;
   Fr k; ld_scalar(k, scalars + i * 32);
   fr_canon_reduce(k);
-  const bool flip = fr_fold_half(k);                       // k <- min(k, r - k): one bit less to recode
+  SignedDigits sd; sd.init(k, c);                          // k <- min(k, r - k): one bit less to recode
   const uint32_t half = 1u << (c - 1);
-  uint32_t carry = 0;
   for (int j = 0; j < W; j++) {
-    uint32_t d = window_at(k.v, j * c, c) + carry;
-    bool negd = d > half;
-    if (negd) { d = (1u << c) - d; carry = 1; } else carry = 0;
+    bool neg;
+    const uint32_t d = sd.next(j, &neg);
     keys[(size_t)j * n + i] = d ? d - 1 : half;            // `half` = discard bucket for zero digits
-    vals[(size_t)j * n + i] = (uint32_t)((uint64_t)j * n_stride + i) | ((negd != flip) ? 0x80000000u : 0u);
+    vals[(size_t)j * n + i] = (uint32_t)((uint64_t)j * n_stride + i) | (neg ? 0x80000000u : 0u);
   }
 }
 

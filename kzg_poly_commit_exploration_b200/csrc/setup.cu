@@ -44,17 +44,6 @@ __global__ void k_powers(Fr s_mont, uint64_t first, uint64_t n, uint32_t K, Fr* 
   }
 }
 
-// ---- signed-digit recoding (c-bit windows) -------------------------------------
-// returns digit j of the canonical scalar k (8 limbs) given the carry into window j
-__device__ __forceinline__ uint32_t window_bits(const uint32_t* k, int bit, int c) {
-  // bits [bit, bit+c) of a 256-bit integer (zero beyond bit 255)
-  int w = bit >> 5, sh = bit & 31;
-  if (w >= 8) return 0;
-  uint64_t lo = k[w];
-  if (w + 1 < 8) lo |= (uint64_t)k[w + 1] << 32;
-  return (uint32_t)(lo >> sh) & ((1u << c) - 1u);
-}
-
 // ---- fixed-base generator multiplication -------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_setup_points(const Fr* __restrict__ scalars, uint64_t n, const G1Affine* __restrict__ gtable,
@@ -63,15 +52,14 @@ k_setup_points(const Fr* __restrict__ scalars, uint64_t n, const G1Affine* __res
   if (i >= n) return;
   Fr k = scalars[i];
   G1Xyzz acc; set_inf(acc);
-  uint32_t carry = 0;
+  SignedDigits sd; sd.init(k, GT_C);
 #pragma unroll 1
   for (int j = 0; j < GT_W; j++) {
-    uint32_t d = window_bits(k.v, j * GT_C, GT_C) + carry;
-    bool negd = d > (uint32_t)GT_HALF;
-    if (negd) { d = (1u << GT_C) - d; carry = 1; } else carry = 0;
+    bool neg;
+    const uint32_t d = sd.next(j, &neg);
     if (d != 0) {
       G1Affine p; ld_affine(p, gtable + (size_t)j * GT_HALF + (d - 1));
-      madd(acc, p, negd);
+      madd(acc, p, neg);
     }
   }
   out[i] = acc;

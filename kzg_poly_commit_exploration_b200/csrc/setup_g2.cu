@@ -60,43 +60,33 @@ k_g2_table(G2Affine* __restrict__ tab) {
   tab[t] = a;
 }
 
-// signed digits of a canonical scalar, folded to min(k, r - k): dig[j] = |d_j| | sign << 31
+// signed digits of a canonical scalar, folded to min(k, r - k): dig[j] = |d_j| | sign << 31 (recode.cuh)
 __device__ __forceinline__ void g2_digits(const Fr& kin, uint32_t* dig) {
-  Fr k = kin;
-  const bool flip = fr_fold_half(k);
-  uint32_t carry = 0;
+  SignedDigits sd; sd.init(kin, G2T_C);
 #pragma unroll 1
   for (int j = 0; j < G2T_W; j++) {
-    const int bit = j * G2T_C, w = bit >> 5, sh = bit & 31;
-    uint64_t lo = k.v[w];
-    if (w + 1 < 8) lo |= (uint64_t)k.v[w + 1] << 32;
-    uint32_t d = ((uint32_t)(lo >> sh) & ((1u << G2T_C) - 1u)) + carry;
-    const bool negd = d > (uint32_t)G2T_HALF;
-    if (negd) { d = (1u << G2T_C) - d; carry = 1; } else carry = 0;
-    dig[j] = d | ((negd != flip) ? 0x80000000u : 0u);
+    bool neg;
+    const uint32_t d = sd.next(j, &neg);
+    dig[j] = d | (neg ? 0x80000000u : 0u);
   }
 }
+
+__device__ __forceinline__ void neg_y(G2Affine& p) { neg(p.y, p.y); }
 
 __global__ void __launch_bounds__(64)
 k_setup_points_g2(const Fr* __restrict__ scalars, uint64_t n, const G2Affine* __restrict__ tab,
                   uint8_t* __restrict__ out_c96) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fr k = scalars[i];
-  const bool flip = fr_fold_half(k);
+  SignedDigits sd; sd.init(scalars[i], G2T_C);
   G2Xyzz acc; set_inf(acc);
-  uint32_t carry = 0;
 #pragma unroll 1
   for (int j = 0; j < G2T_W; j++) {
-    const int bit = j * G2T_C, w = bit >> 5, sh = bit & 31;
-    uint64_t lo = k.v[w];
-    if (w + 1 < 8) lo |= (uint64_t)k.v[w + 1] << 32;
-    uint32_t d = ((uint32_t)(lo >> sh) & ((1u << G2T_C) - 1u)) + carry;
-    const bool negd = d > (uint32_t)G2T_HALF;
-    if (negd) { d = (1u << G2T_C) - d; carry = 1; } else carry = 0;
+    bool neg;
+    const uint32_t d = sd.next(j, &neg);
     if (d != 0) {
       G2Affine p = tab[(size_t)j * G2T_HALF + (d - 1)];
-      if (negd != flip) neg(p.y, p.y);
+      if (neg) neg_y(p);
       madd(acc, p.x, p.y);
     }
   }

@@ -19,7 +19,7 @@ CSRC = os.path.join(ROOT, "kzg_poly_commit_exploration_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def recode_bin():
-    deps = [SRC, os.path.join(CSRC, "field.cuh")]
+    deps = [SRC, os.path.join(CSRC, "field.cuh"), os.path.join(CSRC, "recode.cuh")]
     if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O1", "-I", CSRC, "-x", "c++", SRC, "-o", BIN], check=True)
     return BIN
