@@ -631,6 +631,37 @@ def test_config_c3_msm_2_20(ctx):
     st.close()
 
 
+# ---- BASELINE config C5: 2^22 G1 setup points (affine-tree path, two passes), G2 powers over two passes --------------
+def test_config_c5_setup_2_22(ctx):
+    n = (1 << 22) + 777                               # the trees run in passes of 2^22 items: a full pass + a ragged one
+    st = ctx.setup_generate(SECRET, n)
+    idx = [0, 1, 2, 4095, 65536, (1 << 21) + 12345, (1 << 22) - 1, 1 << 22, (1 << 22) + 1, n - 1]
+    for i in idx:
+        assert st.export_g1(i, 1) == g1c(pow(S, i, O.R)), i
+    # index-range sharding (the multi-GPU layout): a shard generated on its own carries the same bytes
+    first = (1 << 22) - 300
+    sh = ctx.setup_generate(SECRET, 1 << 18, first=first)          # 2^18 items: tree path as well
+    assert sh.export_g1(0, 600) == st.export_g1(first, 600)
+    assert sh.export_g1((1 << 18) - 1, 1) == g1c(pow(S, first + (1 << 18) - 1, O.R))
+    # size-independent property: item i+1 = s * item i (host scalar multiplication of the exported point)
+    import ctypes as C
+    L = native_lib()
+    o = (C.c_uint8 * 48)()
+    s_le = (C.c_uint8 * 32).from_buffer_copy(O.fr_to_le_bytes(S))
+    for i in (777, (1 << 22) - 1, n - 2):
+        a = st.export_g1(i, 2)
+        assert L.kzg_g1_mul((C.c_uint8 * 48).from_buffer_copy(a[:48]), s_le, o) == 0
+        assert bytes(o) == a[48:], i
+    st.close(); sh.close()
+    # G2 powers through the Fq2 trees, passes of 2^20 items
+    m = (1 << 20) + 333
+    st2 = ctx.setup_generate(SECRET, m)
+    st2.generate_g2(SECRET, m)
+    for i in (0, 1, 65535, (1 << 20) - 1, 1 << 20, m - 1):
+        assert st2.export_g2(i, 1) == O.g2_compress(O.g2_from_scalar(pow(S, i, O.R))), i
+    st2.close()
+
+
 def native_lib():
     import kzg_poly_commit_exploration_b200 as pkg
     return pkg.lib()
