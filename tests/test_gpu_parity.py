@@ -631,6 +631,54 @@ def test_config_c3_msm_2_20(ctx):
     st.close()
 
 
+# ---- BASELINE config C4 at FULL size: 4096 blobs x 4096 coefficients through the shipped path ------------------------
+def test_config_c4_full_size_4096_blobs():
+    """kzg_commit_open_batch on the 15-bit fixed-base table (102 GiB, 17 lookups per coefficient), pinned host buffers,
+    chunked staging, commitments and proofs on two lanes: spot blobs against the known-secret identities and a checksum
+    of checksums - the group sum of all 4096 commitments equals the bucket-MSM commitment (another kernel path, another
+    setup object) of the coefficient-wise sum."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import kzg_poly_commit_exploration_b200 as pkg
+    from kzg_poly_commit_exploration_b200 import synthetic
+    n = blobs = 4096
+    c4 = pkg.Context(0)
+    st = c4.setup_generate(SECRET, n)
+    try:
+        st.prepare_fixed(n, 15)
+    except Exception as e:                      # a smaller device: the table does not fit
+        st.close(); c4.close()
+        pytest.skip(f"15-bit fixed-base table not available here: {e}")
+    co = synthetic.scalar_stream(0xC4, blobs * n)                    # (blobs*n, 32) uint8
+    zs = synthetic.scalar_stream(0xC4F, blobs)
+    host = torch.from_numpy(co).pin_memory()
+    zh = torch.from_numpy(zs).pin_memory()
+    commits, ys, proofs = c4.commit_open_batch(st, host.data_ptr(), blobs, n, zh.data_ptr())
+    assert len(commits) == 48 * blobs and len(ys) == 32 * blobs and len(proofs) == 48 * blobs
+    raw = co.tobytes()
+    for b in (0, 1, 255, 256, 2047, 2048, blobs - 1):                # staging chunks: 256 rows, then 2048s
+        row = util.to_ints(raw[b * n * 32: (b + 1) * n * 32])
+        z = int.from_bytes(zs[b].tobytes(), "little")
+        assert commits[48 * b: 48 * b + 48] == O.g1_compress(O.commit_known_secret(row, S)), b
+        assert int.from_bytes(ys[32 * b: 32 * b + 32], "little") == O.horner(row, z), b
+        assert proofs[48 * b: 48 * b + 48] == O.g1_compress(O.proof_known_secret(row, S, z)), b
+    # coefficient-wise sum over the blobs, exact: 32-bit half-limbs summed in uint64 (4096 x 2^32 < 2^44), recombined as ints
+    halves = co.reshape(blobs, n, 32).view(np.uint32).astype(np.uint64).sum(axis=0)       # (n, 8)
+    tot = [sum(int(halves[i, j]) << (32 * j) for j in range(8)) % O.R for i in range(n)]
+    L = native_lib()
+    acc = O.g1_compress(None)
+    o = (C.c_uint8 * 48)()
+    b48 = lambda x: (C.c_uint8 * 48).from_buffer_copy(x)
+    for b in range(blobs):
+        assert L.kzg_g1_add(b48(acc), b48(commits[48 * b: 48 * b + 48]), o) == 0
+        acc = bytes(o)
+    st2 = c4.setup_generate(SECRET, n)                               # no fixed table: bucket MSM
+    assert c4.msm_g1(st2, util.from_ints(tot)) == acc
+    del host, zh
+    st.close(); st2.close(); c4.close()
+
+
 # ---- BASELINE config C5: 2^22 G1 setup points (affine-tree path, two passes), G2 powers over two passes --------------
 def test_config_c5_setup_2_22(ctx):
     n = (1 << 22) + 777                               # the trees run in passes of 2^22 items: a full pass + a ragged one
