@@ -134,3 +134,14 @@ def test_scalar_stream_matches_product_generator():
     a = synthetic.scalar_stream(0xC3, 3000, 17)
     for i in range(3000):
         assert int.from_bytes(a[i].tobytes(), "little") == O.scalar_stream(0xC3, 17 + i)
+
+
+def test_bench_commitment_golden_is_what_bench_asserts():
+    """bench.py compares every timed MSM result with tests/golden/bench_commitment.json's value (embedded as a constant)."""
+    import json
+    import re
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bench_commitment.json")) as f:
+        g = json.load(f)
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    m = re.search(r'GOLDEN_C3_COMMITMENT = "([0-9a-f]{96})"', src)
+    assert m and m.group(1) == g["commit"]

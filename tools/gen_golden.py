@@ -25,4 +25,12 @@ for d in (1, 100, 500, 1000, 1023, 2500):
     }
 with open(os.path.join(ROOT, "tests", "golden", "kat_bench_inputs.json"), "w") as f:
     json.dump(out, f, indent=1)
+# the commitment of bench.py's workload (BASELINE config C3): n = 2^20 scalars U(0xC3, i) over the bench-secret setup,
+# by the known-secret identity [p(s)]G1; bench.py asserts every timed result against it at every GPU count
+sys.path.insert(0, ROOT)
+from kzg_poly_commit_exploration_b200 import synthetic
+raw = synthetic.scalar_stream(0xC3, 1 << 20).tobytes()
+ints = [int.from_bytes(raw[i: i + 32], "little") for i in range(0, len(raw), 32)]
+with open(os.path.join(ROOT, "tests", "golden", "bench_commitment.json"), "w") as f:
+    json.dump({"workload": "n=2^20, scalars U(0xC3,i), secret 00..1f", "commit": O.g1_compress(O.commit_known_secret(ints, s)).hex()}, f, indent=1)
 print("wrote golden vectors")
