@@ -221,6 +221,21 @@ def test_open_errors_and_degree_check(ctx, setup8k, native):
     with pytest.raises(native.KzgNativeError) as ei:
         ctx.open(small, util.from_ints([42]), util.le(7), util.le(41))
     assert ei.value.kind == "CONSTANT_POLY"
+    # batch entry points: same degree rule per blob (more coefficients than setup items), same bytes as the single calls
+    two = util.from_ints([1, 2, 3, 4, 9, 8, 7, 6])
+    zs = util.le(5) + util.le(11)
+    cm, ys, pr = ctx.commit_open_batch(small, two, 2, 4, zs)
+    assert cm[:48] == ctx.commit(small, ok) and cm[48:] == ctx.commit(small, util.from_ints([9, 8, 7, 6]))
+    assert (ys[32:], pr[48:]) == ctx.open(small, util.from_ints([9, 8, 7, 6]), util.le(11))
+    for call in (lambda: ctx.commit_batch(small, util.from_ints([1] * 10), 2, 5),
+                 lambda: ctx.commit_open_batch(small, util.from_ints([1] * 10), 2, 5, zs)):
+        with pytest.raises(native.KzgNativeError) as ei:
+            call()
+        assert ei.value.kind == "DEGREE_TOO_HIGH"
+    fresh = ctx.setup_generate(SECRET, 2)
+    with pytest.raises(native.KzgNativeError):
+        fresh.msm_plan(2)                                   # no MSM table prepared yet
+    fresh.close()
     small.close()
 
 
