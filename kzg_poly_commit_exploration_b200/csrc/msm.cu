@@ -247,8 +247,11 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   void* parts = bk;
   if (logT) KZG_TRY(scratch_get(ctx, SCR_PARTIALS, ((size_t)half << logT) * sizeof(G1Xyzz), &parts));
   {
+    // After the halving rounds this kernel folds only ~16 dense points per bucket: 2^16 threads = 512 blocks, which is
+    // 1.15 waves at 3 blocks per SM but ONE wave at 4 (128 registers; n = 2^17 alone: 1.59 -> 1.55 ms).  Without rounds
+    // (all W n additions here) 3 blocks per SM and 168 registers are faster (profiles/sweep_acc_r01.txt).
     auto kern = k_bucket_acc<3>;
-    if (ctx->opt_acc_minblocks == 4) kern = k_bucket_acc<4>;
+    if (ctx->opt_acc_minblocks == 4 || (ctx->opt_acc_minblocks == 0 && rounds > 0)) kern = k_bucket_acc<4>;
     else if (ctx->opt_acc_minblocks == 5) kern = k_bucket_acc<5>;
     else if (ctx->opt_acc_minblocks == 6) kern = k_bucket_acc<6>;
     if (rounds == 0) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
