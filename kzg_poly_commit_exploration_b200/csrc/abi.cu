@@ -478,7 +478,9 @@ static int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scala
   }
   G1Xyzz* res = reinterpret_cast<G1Xyzz*>(q.result);
   uint8_t* out_dev = reinterpret_cast<uint8_t*>(q.result) + 256;
+  lane->throughput_mode = ctx->lanes_in_use > 1;      // several calls in flight: tuned for throughput, not for the shortest chain
   int32_t st = msm_any(lane, s, dev_scalars, n, res);
+  lane->throughput_mode = false;
   if (st == KZG_OK) {
     if (sharded) st = exchange_combine(lane, ctx, t + 1, res, out_dev, reinterpret_cast<uint32_t*>(out_dev + 48));
     else st = finalize_points(lane, res, 1, out_dev);

@@ -245,7 +245,8 @@ int32_t batch_invert_inplace(kzg_ctx* ctx, Fq* v, uint64_t N, Fq* ws, uint64_t t
     cur = l.up; n = U;
   }
   if (n > 64) {
-    if (ctx->opt_inv_top_fan == 4) {
+    const int fan = ctx->opt_inv_top_fan ? ctx->opt_inv_top_fan : (ctx->throughput_mode ? 8 : 4);
+    if (fan == 4) {
       const uint64_t U = (n + 3) / 4;
       k_inv_top8<4><<<blocks_for(U, 64), 64, 0, ctx->stream>>>(cur, n, U);
     } else {

@@ -52,7 +52,11 @@ struct kzg_ctx {
   int opt_tree_min_rows = 512;         // batches of at least this many rows take the affine tree path (batch_tree.cu)
   int opt_tree_chunk_rows = 2048;      // rows reduced together (bounds the scratch: ~8 KiB * n/4096 * W/2 per row... see DESIGN)
   int64_t opt_tree_min_pairs = 1 << 19;  // stop halving when a round would have fewer independent additions
-  int opt_inv_top_fan = 4;             // values per thread in the fused top kernel (4 or 8; measured: 4)
+  int opt_inv_top_fan = 0;             // values per thread in the fused top kernel of the batch inversion: 4 or 8; 0 = auto:
+                                       // 4 for a call on its own (shortest chain), 8 for calls submitted through the lanes
+                                       // (half as many binary-GCD inversions; n = 2^20: 5.51 -> 5.43 ms with four in flight,
+                                       // 6.45 -> 6.61 ms alone)
+  bool throughput_mode = false;        // set around the MSM of a submitted call (abi.cu submit_common)
   int64_t opt_inv_top = 1 << 18;       // batch inversion: values left for the fused top kernel
   int opt_msm_tree_rounds = -1;        // affine halving rounds before the XYZZ accumulate: -1 = auto (log2(entries) - 19, 0..6)
   int opt_acc_min_entries = 16;        // keep splitting a bucket across threads while a thread still gets more than this
