@@ -1,5 +1,5 @@
 """Short driver for ncu: one 4096-point setup with the 15-bit fixed-base table, `reps` commit+open batches of `blobs`
-blobs x 4096 coefficients on the device.  usage: python tools/prof_blob.py [blobs] [reps] [window_bits]"""
+blobs x 4096 coefficients on the device.  usage: python tools/prof_blob.py [blobs] [reps] [window_bits] [name=value ...]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT]
@@ -11,6 +11,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 c = int(sys.argv[3]) if len(sys.argv) > 3 else 15
 n = 4096
 ctx = pkg.Context(0)
+for kv in sys.argv[4:]:
+    k, v = kv.split("="); ctx.set_option(k, int(v))
 st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, n)
 st.prepare_fixed(n, c)
 dev = torch.device("cuda:0")
