@@ -13,9 +13,15 @@
  *     format (Serialize for G1Point, src/curves.rs:99-110).
  *   - pointers are HOST pointers unless the parameter name ends in _dev (device pointers in
  *     the ctx's CUDA device, e.g. a torch tensor's data_ptr()).
- *   - a kzg_ctx is bound to ONE CUDA device and is externally synchronised (one caller at a
- *     time).  Multi-GPU = one process (or ctx) per GPU; partial results are exchanged by the
- *     host (NCCL all-gather of kzg_g1_partial blobs) and folded with kzg_g1_combine.
+ *   - a kzg_ctx is externally synchronised (one caller at a time) and is either bound to ONE CUDA
+ *     device (kzg_ctx_create) or drives SEVERAL devices from one host process
+ *     (kzg_ctx_create_multi): the same calls then shard internally — one sum by point range
+ *     with the partial sums exchanged over NVLink peer memory, batches by row, setup generation
+ *     by index range — which is what a single-process host like the reference
+ *     (src/main.rs:170) needs to reach every GPU of the node.  The one-process-per-GPU mode
+ *     (kzg_p2p_* + kzg_msm_g1_sharded_*, or NCCL all-gather of kzg_g1_partial blobs folded with
+ *     kzg_g1_combine_dev) serves torchrun / MPI style hosts.
+ *   - setups must be destroyed before the context they were created on.
  *   - there is NO CPU fallback for bulk operations: without a CUDA device kzg_ctx_create
  *     fails with KZG_E_CUDA.  The kzg_fr_* / kzg_g1_* single-element helpers are host code
  *     (they replace per-element blst calls of the public Rust API, not the hot path).
@@ -51,6 +57,21 @@ typedef enum {
 
 /* ---- context ------------------------------------------------------------------------- */
 int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id);
+/* One context over n_dev devices of this process (1 <= n_dev <= 32; all pairs need peer access: NVLink / NVSwitch).
+ * Every call below works on it unchanged; what changes is where the work runs:
+ *   kzg_setup_generate / _import_g1 : up to 2^16 points the setup is REPLICATED on every device (the blob-batch shape),
+ *        above that it is SHARDED BY POINT RANGE, device g holding items [g n/N, (g+1) n/N) (option "setup_layout":
+ *        0 auto, 1 range, 2 replicated);
+ *   kzg_commit / kzg_msm_g1 / _submit / kzg_open : range-sharded setup: every device sums its range, ONE kernel per
+ *        device stores the 192-byte partial into every peer's mailbox, waits, folds and compresses (no NCCL, no second
+ *        process); replicated setup: device 0;
+ *   kzg_*_batch : rows split evenly over the devices (replicated setup), no exchange;
+ *   kzg_evaluate / kzg_quotient : device 0 (a single polynomial's scan does not shard).
+ * Device pointers (`_dev` parameters) may live on any device of the group.  The kzg_p2p_* / kzg_msm_g1_sharded_* /
+ * kzg_msm_g1_partial_dev calls belong to the one-process-per-GPU mode and return KZG_E_BAD_ARG here.
+ * Listing one device twice is allowed (two members share it): it exercises the whole path on a single-GPU box. */
+int32_t kzg_ctx_create_multi(kzg_ctx** out, const int32_t* device_ids, int32_t n_dev);
+int32_t kzg_ctx_device_count(const kzg_ctx* ctx);
 void kzg_ctx_destroy(kzg_ctx* ctx);
 const char* kzg_last_error(const kzg_ctx* ctx);
 const char* kzg_status_string(int32_t status);
@@ -105,6 +126,10 @@ void kzg_setup_destroy(kzg_setup* s);
  *                            (bucket-free fixed-base commit used for blob batches)           */
 int32_t kzg_setup_prepare_msm(kzg_ctx* ctx, kzg_setup* s, int32_t window_bits);
 int32_t kzg_setup_prepare_fixed(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int32_t window_bits);
+/* window_bits = 0 picks the widest window (<= 15) whose table fits the memory budget: option "fixed_table_max_bytes",
+ * else 60 % of the device memory free at the time (blob throughput is ~ 1 / ceil(255 / c); n = 4096: c = 15 is 102 GiB,
+ * c = 14 51 GiB, c = 13 26 GiB).  plan = { window_bits c, lookups per coefficient W, points covered, table bytes }. */
+int32_t kzg_setup_fixed_plan(const kzg_setup* s, int64_t plan[4]);
 
 /* ---- commit / evaluate / open ----------------------------------------------------------
  * Coefficients: n x 32-byte LE, ascending degree; trailing zero coefficients are trimmed as
@@ -167,14 +192,18 @@ int32_t kzg_msm_g1_partial_dev(kzg_ctx* ctx, const kzg_setup* s, const void* sca
  *   kzg_p2p_connect  takes the handles of ALL ranks, rank-major (world x KZG_P2P_HANDLE_BYTES; how they travel
  *                    between the processes is the caller's business: torch.distributed, MPI, a file ...);
  *   kzg_msm_g1_sharded_dev  is collective: every rank calls it with its shard, every rank receives the full result.
- * A rank that never shows up turns into KZG_E_CUDA after ~2 s instead of a hang. */
+ * A rank that never shows up turns into KZG_E_CUDA after 20 s (option "p2p_timeout_ms") instead of a hang, and it does so
+ * on EVERY rank: the rank that gives up leaves a sticky mark in all mailboxes, so a peer that arrives late fails too
+ * instead of returning a result alone; the contexts then refuse further collective calls.  Build the tables
+ * (kzg_setup_prepare_msm) and rendezvous on the host before the first collective call: a lazy 2 GiB table build on one
+ * rank is exactly the kind of skew the timeout is for.  Collective calls are numbered by their own counter: every rank
+ * must issue the same sequence of kzg_msm_g1_sharded_* calls (other calls in between do not matter). */
 #define KZG_P2P_HANDLE_BYTES 64
 int32_t kzg_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_out[KZG_P2P_HANDLE_BYTES]);
 int32_t kzg_p2p_connect(kzg_ctx* ctx, const uint8_t* handles);
 int32_t kzg_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,
                                uint8_t out_c48[48]);
-/* the same with up to `lanes` collective calls in flight (collect with kzg_msm_g1_wait); the ticket numbers are the
- * collective's sequence numbers, so every rank must issue the same sequence of submit calls on its context */
+/* the same with up to `lanes` collective calls in flight (collect with kzg_msm_g1_wait) */
 int32_t kzg_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n,
                                       int32_t* ticket);
 /* ... and with this rank's shard of the scalars in a HOST buffer (copied on the lane's copy stream, like kzg_msm_g1_submit) */
@@ -185,6 +214,9 @@ int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t coun
                            uint8_t out_c48[48]);
 int32_t kzg_commit_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev,
                              uint64_t blobs, uint64_t n, void* out_c48_dev);
+/* Batches compare the TRIMMED length of the longest row with the setup, like Polynomial::commit
+ * (src/polynomial.rs:201-205): rows may be longer than the setup when the excess is zero padding (the _dev variants
+ * then spend one pass and one synchronisation on the check).  Any number of rows. */
 int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev,
                            uint64_t blobs, uint64_t n, const void* z_dev, void* y_dev,
                            void* proofs_c48_dev);
@@ -227,8 +259,9 @@ int32_t kzg_verify_proof(const uint8_t proof[48], const uint8_t commitment[48], 
                          const uint8_t y_le[32], const uint8_t g2_tau[96], int32_t* ok);
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
-/* integer-pipe roofline probe: independent 32x32+64 multiply-add chains on every SM;
- * returns wide multiply-adds per second (BASELINE.md §4 "measured integer peak") */
+/* integer-pipe roofline probe: independent 32x32->64 products (IMAD.WIDE.U32, zero addend) on every SM, each folded
+ * back with one LOP3; returns wide multiplies per second = the issue rate of the multiplier pipe (BASELINE.md §4
+ * "measured integer peak"; nominal 64 lanes / clk / SM).  The additions of a multiply-ACCUMULATE come on top. */
 int32_t kzg_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s);
 /* sustained Montgomery Fq multiplications per second of the shipped field kernel (all SMs busy) */
 int32_t kzg_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s);

@@ -30,6 +30,12 @@ class Context {
     int32_t st = kzg_ctx_create(&h_, device);
     if (st != KZG_OK) throw Error(st, "kzg_ctx_create failed: no usable CUDA device (there is no CPU fallback)");
   }
+  // several devices driven from this process (kzg_ctx_create_multi): the same calls shard internally
+  explicit Context(const std::vector<int32_t>& devices) {
+    int32_t st = kzg_ctx_create_multi(&h_, devices.data(), (int32_t)devices.size());
+    if (st != KZG_OK) throw Error(st, "kzg_ctx_create_multi failed: no usable CUDA devices or no peer access between them");
+  }
+  int device_count() const { return kzg_ctx_device_count(h_); }
   ~Context() { kzg_ctx_destroy(h_); }
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;

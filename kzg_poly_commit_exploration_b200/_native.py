@@ -23,6 +23,8 @@ _i32 = C.c_int32
 # name -> (restype, argtypes); every symbol include/kzg_b200.h declares
 SIGNATURES = {
     "kzg_ctx_create": (_i32, [C.POINTER(_vp), _i32]),
+    "kzg_ctx_create_multi": (_i32, [C.POINTER(_vp), C.POINTER(_i32), _i32]),
+    "kzg_ctx_device_count": (_i32, [_vp]),
     "kzg_ctx_destroy": (None, [_vp]),
     "kzg_last_error": (C.c_char_p, [_vp]),
     "kzg_status_string": (C.c_char_p, [_i32]),
@@ -45,6 +47,7 @@ SIGNATURES = {
     "kzg_setup_destroy": (None, [_vp]),
     "kzg_setup_prepare_msm": (_i32, [_vp, _vp, _i32]),
     "kzg_setup_prepare_fixed": (_i32, [_vp, _vp, _u64, _i32]),
+    "kzg_setup_fixed_plan": (_i32, [_vp, C.POINTER(C.c_int64)]),
     "kzg_commit": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "kzg_evaluate": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "kzg_quotient": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, C.POINTER(_u64)]),

@@ -1,884 +1,697 @@
-// extern "C" boundary of libkzg_b200.so (include/kzg_b200.h): context, setup objects and the bulk
-// operations.  Semantics (trimming, error cases) mirror the reference's public API:
-//   Polynomial::try_from / degree / commit / evaluate / sub / divide_by_root  src/polynomial.rs:38-215
-//   Evaluation::generate_proof                                                 src/polynomial.rs:260-269
-//   SetupArtifactsGenerator                                                    src/trusted_setup.rs:20-78
-// There is no CPU fallback for any bulk operation.
+// extern "C" boundary of libkzg_b200.so (include/kzg_b200.h).
+//
+// A context is either ONE CUDA device (kzg_ctx_create; every entry point forwards to the single-device engine,
+// engine_one.cu) or a GROUP of devices driven by one host caller (kzg_ctx_create_multi) — the shape of the reference,
+// which is a single process (src/main.rs:170, benches/polynomial_commitment.rs:38-47): a Rust Polynomial::commit
+// linked against this library reaches every GPU of the node without torchrun, NCCL or a second process.
+//
+// Group layout:
+//   * a setup is sharded by POINT RANGE (member g holds bases [off_g, off_g+1)) or REPLICATED (small setups: blob batches);
+//   * one MSM  = every member's partial sum over its range, exchanged and folded by k_exchange_combine (msm_tail.cu)
+//                over plain peer pointers (cudaDeviceEnablePeerAccess; NVLink 5 / NVSwitch) — the same kernel the
+//                one-process-per-GPU mode runs over CUDA IPC mappings;
+//   * a batch  = rows split by member, no exchange;  setup generation = index range per member, no exchange;
+//   * evaluate / quotient of one polynomial: member 0 (replicas only).
+// Every member has a host worker thread that issues its launches (a chain of ~45 launches costs the host ~0.1 ms: eight
+// devices fed from one thread would be launch-bound at n = 2^20), so one caller drives all devices in parallel.
+// Device pointers passed to a group may live on any member device: the kernels read them over NVLink.
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include "engine.cuh"
 
 using namespace kzg;
 
-namespace kzg {
-
-int32_t scratch_get(kzg_ctx* ctx, int slot, size_t bytes, void** out) {
-  if (bytes == 0) bytes = 16;
-  if (ctx->scratch_cap[slot] < bytes) {
-    if (ctx->scratch[slot]) {
-      KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->scratch[slot]);
-      ctx->scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0;
-    }
-    size_t cap = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
-    cudaError_t e = cudaMalloc(&ctx->scratch[slot], cap);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      ctx->err = "cudaMalloc(scratch): " + std::string(cudaGetErrorString(e));
-      return KZG_E_NOMEM;
-    }
-    ctx->scratch_cap[slot] = cap;
-  }
-  *out = ctx->scratch[slot];
-  return KZG_OK;
-}
-
-int32_t pinned_get(kzg_ctx* ctx, size_t bytes, void** out) {
-  if (ctx->pinned_cap < bytes) {
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    ctx->pinned = nullptr; ctx->pinned_cap = 0;
-    KZG_CUDA_OK(ctx, cudaMallocHost(&ctx->pinned, bytes));
-    ctx->pinned_cap = bytes;
-  }
-  *out = ctx->pinned;
-  return KZG_OK;
-}
-
-}  // namespace kzg
-
 namespace {
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+// ---- host worker: one per member >= 1 (member 0 runs on the caller's thread) ------------------------------------------
+class Worker {
+ public:
+  explicit Worker(int device) : device_(device), th_([this] { run(); }) {}
+  ~Worker() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    th_.join();
+  }
+  void post(std::function<void()> job) {
+    { std::lock_guard<std::mutex> l(m_); job_ = std::move(job); has_job_ = true; done_ = false; }
+    cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> l(m_);
+    cv_done_.wait(l, [this] { return done_; });
+  }
+
+ private:
+  void run() {
+    cudaSetDevice(device_);
+    std::unique_lock<std::mutex> l(m_);
+    for (;;) {
+      cv_.wait(l, [this] { return has_job_ || stop_; });
+      if (stop_) return;
+      std::function<void()> job = std::move(job_);
+      has_job_ = false;
+      l.unlock();
+      job();
+      l.lock();
+      done_ = true;
+      cv_done_.notify_all();
+    }
+  }
+  int device_;
+  std::mutex m_;
+  std::condition_variable cv_, cv_done_;
+  std::function<void()> job_;
+  bool has_job_ = false, stop_ = false, done_ = true;
+  std::thread th_;
 };
 
-// value == 0 mod r  <=>  value in {0, r, 2r} (2^256 < 3r)
-bool le32_is_zero_mod_r(const uint8_t* b) {
-  Fr a; fr_load_le(a, b); fr_canon_reduce(a);
-  return is_zero(a);
+struct GroupTicket {
+  int32_t member_ticket[KZG_MAX_PEERS];
+  bool busy = false;
+};
+
+struct GroupState {
+  std::vector<std::unique_ptr<Worker>> workers;     // workers[g - 1] serves member g
+  GroupTicket tickets[KZG_MAX_LANES];
+};
+
+inline bool is_group(const kzg_ctx* ctx) { return ctx && !ctx->members.empty(); }
+inline GroupState* gs(kzg_ctx* head) { return reinterpret_cast<GroupState*>(head->group_state); }
+inline int group_size(const kzg_ctx* ctx) { return (int)ctx->members.size(); }
+
+// fn(g, member) on every member at once (member 0 on this thread); the first failure wins and its message moves to the head
+int32_t for_members(kzg_ctx* head, const std::function<int32_t(int, kzg_ctx*)>& fn) {
+  const int G = group_size(head);
+  std::vector<int32_t> st((size_t)G, KZG_OK);
+  GroupState* S = gs(head);
+  for (int g = 1; g < G; g++) S->workers[(size_t)g - 1]->post([&, g] { st[(size_t)g] = fn(g, head->members[(size_t)g]); });
+  st[0] = fn(0, head);
+  for (int g = 1; g < G; g++) S->workers[(size_t)g - 1]->wait();
+  for (int g = 0; g < G; g++) {
+    if (st[(size_t)g] == KZG_OK) continue;
+    if (g) head->err = "device " + std::to_string(head->members[(size_t)g]->device) + ": " + head->members[(size_t)g]->err;
+    return st[(size_t)g];
+  }
+  return KZG_OK;
 }
-// Polynomial::try_from trimming (src/polynomial.rs:63-72): number of coefficients up to the last
-// non-zero one; 0 when every coefficient is zero (the reference keeps one zero coefficient then,
-// which evaluates / commits identically to none).
-uint64_t trimmed_len(const uint8_t* coeffs, uint64_t n) {
-  while (n > 0 && le32_is_zero_mod_r(coeffs + (n - 1) * 32)) n--;
+
+// contiguous ranges of n items over G members, remainders to the low members (parallel.shard_range on the Python side)
+std::vector<uint64_t> shard_offsets(uint64_t n, int G) {
+  std::vector<uint64_t> off((size_t)G + 1, 0);
+  const uint64_t base = n / (uint64_t)G, rem = n % (uint64_t)G;
+  for (int g = 0; g < G; g++) off[(size_t)g + 1] = off[(size_t)g] + base + ((uint64_t)g < rem ? 1 : 0);
+  return off;
+}
+
+// part of [0, n) that falls into shard g of a range-sharded setup
+inline uint64_t shard_share(const kzg_setup* S, int g, uint64_t n) {
+  const uint64_t lo = S->shard_off[(size_t)g], hi = S->shard_off[(size_t)g + 1];
+  return n <= lo ? 0 : std::min(n, hi) - lo;
+}
+
+int choose_layout(const kzg_ctx* head, uint64_t n) {
+  if (head->opt_setup_layout == 1 || head->opt_setup_layout == 2) return head->opt_setup_layout;
+  return n <= (1u << 16) ? 2 : 1;      // small setups (blob batches: 4096 points) are replicated, large ones sharded by range
+}
+
+kzg_setup* new_group_setup(kzg_ctx* head, uint64_t n, int layout) {
+  kzg_setup* S = new kzg_setup();
+  S->ctx = head; S->n = n; S->layout = layout;
+  S->shards.assign((size_t)group_size(head), nullptr);
+  S->shard_off = layout == 1 ? shard_offsets(n, group_size(head)) : std::vector<uint64_t>((size_t)group_size(head) + 1, 0);
+  if (layout == 2) for (size_t g = 1; g < S->shard_off.size(); g++) S->shard_off[g] = n;   // every shard: all n items
+  return S;
+}
+
+void destroy_group_setup(kzg_setup* S) {
+  for (kzg_setup* sh : S->shards) if (sh) one_setup_destroy(sh);
+  delete S;
+}
+
+bool setup_matches(const kzg_ctx* ctx, const kzg_setup* s) {
+  return s && (is_group(ctx) ? (s->layout != 0 && s->ctx == ctx) : s->layout == 0);
+}
+
+#define KZG_CHECK_SETUP(ctx, s)                                                                                   \
+  do {                                                                                                            \
+    if (!setup_matches(ctx, s)) return fail(ctx, KZG_E_BAD_ARG, "this setup belongs to another kind of context"); \
+  } while (0)
+
+int32_t group_create(kzg_ctx** out, const int32_t* ids, int32_t n) {
+  std::vector<kzg_ctx*> m;
+  auto undo = [&m] { for (kzg_ctx* c : m) one_ctx_destroy(c); };
+  for (int g = 0; g < n; g++) {
+    kzg_ctx* c = nullptr;
+    int32_t st = one_ctx_create(&c, ids[g]);
+    if (st != KZG_OK) { undo(); return st; }
+    m.push_back(c);
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  // every member reads and writes every other member's memory (mailboxes, scalars, results): plain peer access
+  for (int a = 0; a < n; a++) {
+    for (int b = 0; b < n; b++) {
+      if (ids[a] == ids[b]) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ids[a], ids[b]) != cudaSuccess || !can) {
+        cudaGetLastError(); cudaSetDevice(prev); undo();
+        return KZG_E_CUDA;          // no NVLink / PCIe peer path between two of the devices
+      }
+      cudaSetDevice(ids[a]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(ids[b], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); cudaSetDevice(prev); undo(); return KZG_E_CUDA; }
+      cudaGetLastError();
+    }
+  }
+  void* boxes[KZG_MAX_PEERS] = {};
+  for (int g = 0; g < n; g++) {
+    cudaSetDevice(ids[g]);
+    int32_t st = p2p_alloc_box(m[(size_t)g], n, g);
+    if (st != KZG_OK) { cudaSetDevice(prev); undo(); return st; }
+    boxes[g] = m[(size_t)g]->p2p_box[g];
+  }
+  for (int g = 0; g < n; g++) p2p_attach_local(m[(size_t)g], boxes);
+  cudaSetDevice(prev);
+  kzg_ctx* head = m[0];
+  GroupState* S = new GroupState();
+  for (int g = 1; g < n; g++) S->workers.emplace_back(new Worker(ids[g]));
+  head->group_state = S;
+  head->members = m;
+  for (kzg_ctx* c : m) c->group_head = head;
+  *out = head;
+  return KZG_OK;
+}
+
+void group_destroy(kzg_ctx* head) {
+  for (kzg_ctx* c : head->members) one_ctx_sync(c);
+  delete gs(head);                       // joins the workers
+  head->group_state = nullptr;
+  std::vector<kzg_ctx*> m = head->members;
+  head->members.clear();
+  for (size_t g = 1; g < m.size(); g++) one_ctx_destroy(m[g]);
+  one_ctx_destroy(head);
+}
+
+// ---- one MSM on a group --------------------------------------------------------------------------------------------
+// `scalars` is a host buffer (host == true) or a device pointer on any member device; *ticket = the head's ticket
+int32_t group_msm_submit(kzg_ctx* head, const kzg_setup* S, const void* scalars, uint64_t n, bool host, int32_t* ticket) {
+  if (n > S->n) return fail(head, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  const int G = group_size(head);
+  const int L = std::min(KZG_MAX_LANES, std::max(1, head->lanes_in_use ? head->lanes_in_use : head->opt_lanes));
+  GroupTicket& T = gs(head)->tickets[head->next_ticket % (uint32_t)L];
+  if (T.busy) return fail(head, KZG_E_BAD_ARG, "every lane has a call in flight: wait for the oldest ticket first");
+  for (int g = 0; g < G; g++) T.member_ticket[g] = -1;
+  // a replicated setup, or a sum that lives entirely in member 0's range: that device alone, no exchange
+  if (S->layout == 2 || n <= S->shard_off[1]) {
+    KZG_TRY(submit_common(head, S->shards[0], scalars, n, host, false, &T.member_ticket[0]));
+  } else {
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(scalars);
+    int32_t st = for_members(head, [&](int g, kzg_ctx* m) {
+      return submit_common(m, S->shards[(size_t)g], base + S->shard_off[(size_t)g] * 32, shard_share(S, g, n), host, true,
+                           &T.member_ticket[g]);
+    });
+    if (st != KZG_OK) {        // some members may have queued their part: drain them, the group is out of step for good
+      uint8_t sink[48];
+      for (int g = 0; g < G; g++) {
+        if (T.member_ticket[g] >= 0) one_msm_g1_wait(head->members[(size_t)g], T.member_ticket[g], sink);
+        head->members[(size_t)g]->p2p_failed = true;
+      }
+      return st;
+    }
+  }
+  T.busy = true;
+  *ticket = T.member_ticket[0];
+  return KZG_OK;
+}
+
+int32_t group_msm_wait(kzg_ctx* head, int32_t ticket, uint8_t out_c48[48]) {
+  if (ticket < 0) return KZG_E_BAD_ARG;
+  const int L = std::max(1, head->lanes_in_use);
+  GroupTicket& T = gs(head)->tickets[(uint32_t)ticket % (uint32_t)L];
+  if (!T.busy || T.member_ticket[0] != ticket) return fail(head, KZG_E_BAD_ARG, "no call in flight under this ticket");
+  T.busy = false;
+  int32_t first_err = KZG_OK;
+  uint8_t sink[48];
+  for (int g = group_size(head) - 1; g >= 0; g--) {      // every member computed the fold; member 0's copy is the answer
+    if (T.member_ticket[g] < 0) continue;
+    int32_t st = one_msm_g1_wait(head->members[(size_t)g], T.member_ticket[g], g == 0 ? out_c48 : sink);
+    if (st != KZG_OK && first_err == KZG_OK) {
+      first_err = st;
+      if (g) head->err = "device " + std::to_string(head->members[(size_t)g]->device) + ": " + head->members[(size_t)g]->err;
+    }
+  }
+  return first_err;
+}
+
+int32_t group_msm(kzg_ctx* head, const kzg_setup* S, const void* scalars, uint64_t n, bool host, uint8_t out_c48[48]) {
+  int32_t t = -1;
+  KZG_TRY(group_msm_submit(head, S, scalars, n, host, &t));
+  return group_msm_wait(head, t, out_c48);
+}
+
+// host-side trimming of Polynomial::try_from (src/polynomial.rs:63-72), as engine_one.cu does for one device
+uint64_t trimmed_len_host(const uint8_t* coeffs, uint64_t n) {
+  while (n > 0) {
+    Fr a; fr_load_le(a, coeffs + (n - 1) * 32); fr_canon_reduce(a);
+    if (!is_zero(a)) break;
+    n--;
+  }
   return n;
 }
 
-int32_t ensure_msm_table(kzg_ctx* ctx, const kzg_setup* s) {
-  if (s->msm_tab) return KZG_OK;
-  return build_msm_table(ctx, const_cast<kzg_setup*>(s), 0);
+// rows of a batch over the members of a group: member g takes rows [off_g, off_g+1)
+template <typename F>
+int32_t group_rows(kzg_ctx* head, uint64_t blobs, F&& fn) {
+  const std::vector<uint64_t> off = shard_offsets(blobs, group_size(head));
+  return for_members(head, [&](int g, kzg_ctx* m) {
+    const uint64_t r0 = off[(size_t)g], rows = off[(size_t)g + 1] - r0;
+    return rows ? fn(g, m, r0, rows) : (int32_t)KZG_OK;
+  });
 }
 
-// one MSM over the first n bases with device scalars -> XYZZ on device
-int32_t msm_any(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n, G1Xyzz* out_dev) {
-  if (s->fix_tab && n <= s->fix_n && n > 0) return msm_fixed_batch(ctx, s, scalars_dev, 1, n, n, out_dev);
-  KZG_TRY(ensure_msm_table(ctx, s));
-  return msm_bucket(ctx, s, scalars_dev, n, out_dev);
-}
-
-int32_t finish_one(kzg_ctx* ctx, const G1Xyzz* pt_dev, uint8_t out_c48[48]) {
-  void* o;
-  KZG_TRY(scratch_get(ctx, SCR_OUT, 256, &o));
-  KZG_TRY(finalize_points(ctx, pt_dev, 1, reinterpret_cast<uint8_t*>(o)));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c48, o, 48, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  return KZG_OK;
-}
-
-void update_timers(kzg_ctx* ctx) {
-  float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_ms[0] = ms;
-  if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->last_ms[1] = ms;
-  if (cudaEventElapsedTime(&ms, ctx->ev_k[0], ctx->ev_k[1]) == cudaSuccess) ctx->last_ms[2] = ms;
-  cudaGetLastError();
-}
+inline const uint8_t* cu8(const void* p) { return reinterpret_cast<const uint8_t*>(p); }
+inline uint8_t* u8(void* p) { return reinterpret_cast<uint8_t*>(p); }
 
 }  // namespace
 
 extern "C" {
 
-int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id) {
-  if (!out) return KZG_E_BAD_ARG;
+// ---- context ---------------------------------------------------------------------------------------------------------
+int32_t kzg_ctx_create(kzg_ctx** out, int32_t device_id) { return one_ctx_create(out, device_id); }
+
+int32_t kzg_ctx_create_multi(kzg_ctx** out, const int32_t* device_ids, int32_t n_dev) {
+  if (!out || !device_ids || n_dev < 1 || n_dev > KZG_MAX_PEERS) return KZG_E_BAD_ARG;
   *out = nullptr;
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device_id < 0 || device_id >= count) {
-    cudaGetLastError();
-    return KZG_E_CUDA;  // no CPU fallback: the engine needs a CUDA device
-  }
-  kzg_ctx* ctx = new kzg_ctx();
-  ctx->device = device_id;
-  if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KZG_E_CUDA; }
-  for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
-  for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
-  for (int i = 0; i < 4; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
-  for (int i = 0; i < 2; i++) { cudaEventCreate(&ctx->ev_t[i]); cudaEventRecord(ctx->ev_t[i], ctx->stream); }
-  for (int i = 0; i < 2; i++) { cudaEventCreate(&ctx->ev_k[i]); cudaEventRecord(ctx->ev_k[i], ctx->stream); }
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-  cudaStreamSynchronize(ctx->stream);
-  *out = ctx;
-  return KZG_OK;
+  if (n_dev == 1) return one_ctx_create(out, device_ids[0]);
+  return group_create(out, device_ids, n_dev);
 }
+
+int32_t kzg_ctx_device_count(const kzg_ctx* ctx) { return !ctx ? 0 : (is_group(ctx) ? group_size(ctx) : 1); }
 
 void kzg_ctx_destroy(kzg_ctx* ctx) {
-  if (!ctx) return;
-  DeviceGuard g(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < SCR_COUNT; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  for (auto& q : ctx->pending) {
-    if (q.scalars) cudaFree(q.scalars);
-    if (q.result) cudaFree(q.result);
-    if (q.out_host) cudaFreeHost(q.out_host);
-    if (q.copied) cudaEventDestroy(q.copied);
-    if (q.done) cudaEventDestroy(q.done);
-  }
-  for (int r = 0; r < ctx->p2p_world; r++) {
-    if (!ctx->p2p_box[r]) continue;
-    if (r == ctx->p2p_rank) cudaFree(ctx->p2p_box[r]); else cudaIpcCloseMemHandle(ctx->p2p_box[r]);
-  }
-  for (int l = 1; l < KZG_MAX_LANES; l++) if (ctx->lane[l]) kzg_ctx_destroy(ctx->lane[l]);
-  if (ctx->gtable) cudaFree(ctx->gtable);
-  if (ctx->g2table) cudaFree(ctx->g2table);
-  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  for (int i = 0; i < 2; i++) if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
-  for (int i = 0; i < 2; i++) if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
-  for (int i = 0; i < 8; i++) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
-  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  if (is_group(ctx)) group_destroy(ctx); else one_ctx_destroy(ctx);
 }
 
-const char* kzg_last_error(const kzg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+const char* kzg_last_error(const kzg_ctx* ctx) { return one_last_error(ctx); }
 
 int32_t kzg_ctx_sync(kzg_ctx* ctx) {
-  DeviceGuard g(ctx->device);
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  for (int l = 1; l < KZG_MAX_LANES; l++) if (ctx->lane[l]) KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->lane[l]->stream));
-  update_timers(ctx);
+  if (!ctx) return KZG_E_BAD_ARG;
+  if (!is_group(ctx)) return one_ctx_sync(ctx);
+  for (kzg_ctx* m : ctx->members) {
+    int32_t st = one_ctx_sync(m);
+    if (st != KZG_OK) { if (m != ctx) ctx->err = m->err; return st; }
+  }
   return KZG_OK;
 }
 
+void* kzg_ctx_stream(const kzg_ctx* ctx) { return one_ctx_stream(ctx); }
+
+uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) {
+  if (!ctx) return 0;
+  if (!is_group(ctx)) return one_ctx_launch_count(ctx);
+  uint64_t c = 0;
+  for (const kzg_ctx* m : ctx->members) c += one_ctx_launch_count(m);
+  return c;
+}
+
+float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which) { return ctx ? one_ctx_last_kernel_ms(ctx, which) : 0.f; }
+
+// group: the interval is timed on every member's own device and the longest one is reported
 int32_t kzg_ctx_timer_start(kzg_ctx* ctx) {
-  DeviceGuard g(ctx->device);
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_t[0], ctx->stream));
+  if (!ctx) return KZG_E_BAD_ARG;
+  if (!is_group(ctx)) return one_ctx_timer_start(ctx);
+  for (kzg_ctx* m : ctx->members) KZG_TRY(one_ctx_timer_start(m));
   return KZG_OK;
 }
 
 int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
-  DeviceGuard g(ctx->device);
-  for (int l = 1; l < KZG_MAX_LANES; l++) {     // the interval ends when EVERY lane is done
-    if (!ctx->lane[l]) continue;
-    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->lane[l]->ev_t[1], ctx->lane[l]->stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane[l]->ev_t[1], 0));
+  if (!ctx || !ms) return KZG_E_BAD_ARG;
+  if (!is_group(ctx)) return one_ctx_timer_stop(ctx, ms);
+  float worst = 0.f;
+  for (kzg_ctx* m : ctx->members) {
+    float t = 0.f;
+    int32_t st = one_ctx_timer_stop(m, &t);
+    if (st != KZG_OK) { if (m != ctx) ctx->err = m->err; return st; }
+    worst = std::max(worst, t);
   }
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_t[1], ctx->stream));
-  KZG_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_t[1]));
-  KZG_CUDA_OK(ctx, cudaEventElapsedTime(ms, ctx->ev_t[0], ctx->ev_t[1]));
+  *ms = worst;
   return KZG_OK;
-}
-
-uint64_t kzg_ctx_launch_count(const kzg_ctx* ctx) {
-  uint64_t c = ctx->launches;
-  for (int l = 1; l < KZG_MAX_LANES; l++) if (ctx->lane[l]) c += ctx->lane[l]->launches;
-  return c;
-}
-
-void* kzg_ctx_stream(const kzg_ctx* ctx) { return ctx ? reinterpret_cast<void*>(ctx->stream) : nullptr; }
-
-float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which) {
-  return (which >= 0 && which <= 2) ? ctx->last_ms[which] : 0.f;
 }
 
 int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
-  std::string n(name ? name : "");
-  if (n == "msm_window_bits") ctx->opt_msm_window = (int)value;
-  else if (n == "fixed_window_bits") ctx->opt_fixed_window = (int)value;
-  else if (n == "reduce_chunk") ctx->opt_reduce_chunk = (int)value;
-  else if (n == "acc_split") ctx->opt_acc_split = (int)value;
-  else if (n == "acc_min_entries") ctx->opt_acc_min_entries = (int)std::max<int64_t>(1, value);
-  else if (n == "coop_tail") ctx->opt_coop_tail = (int)value;
-  else if (n == "tree_k") ctx->opt_tree_k = (int)value;
-  else if (n == "p2p_timeout_ms") ctx->p2p_timeout_cycles = std::max<int64_t>(1, value) * 2000000ll;   // ~2 GHz
-  else if (n == "acc_minblocks") ctx->opt_acc_minblocks = (int)value;
-  else if (n == "inv_top_fan") ctx->opt_inv_top_fan = (int)value;
-  else if (n == "inv_top") ctx->opt_inv_top = std::max<int64_t>(8, value);
-  else if (n == "msm_tree_rounds") ctx->opt_msm_tree_rounds = (int)value;
-  else if (n == "tree_min_rows") ctx->opt_tree_min_rows = (int)value;
-  else if (n == "tree_chunk_rows") ctx->opt_tree_chunk_rows = (int)value;
-  else if (n == "tree_min_pairs") ctx->opt_tree_min_pairs = value;
-  else if (n == "setup_tree_min") ctx->opt_setup_tree_min = (int)value;
-  else if (n == "lanes") {
-    if (ctx->lanes_in_use) return fail(ctx, KZG_E_BAD_ARG, "the number of lanes is fixed once a call has been submitted");
-    ctx->opt_lanes = (int)std::min<int64_t>(KZG_MAX_LANES, std::max<int64_t>(1, value));
+  if (!ctx) return KZG_E_BAD_ARG;
+  if (!is_group(ctx)) return one_ctx_set_option(ctx, name, value);
+  for (kzg_ctx* m : ctx->members) {
+    int32_t st = one_ctx_set_option(m, name, value);
+    if (st != KZG_OK) { if (m != ctx) ctx->err = m->err; return st; }
   }
-  else if (n == "heavy_cap") ctx->opt_heavy_cap = (int)std::max<int64_t>(1, value);
-  else return fail(ctx, KZG_E_BAD_ARG, "unknown option");
   return KZG_OK;
 }
 
-// ---- setup ---------------------------------------------------------------------------------
-static int32_t setup_alloc(kzg_ctx* ctx, uint64_t n, kzg_setup** out) {
-  kzg_setup* s = new kzg_setup();
-  s->ctx = ctx; s->n = n;
-  if (n) {
-    cudaError_t e = cudaMalloc(&s->bases, n * sizeof(G1Affine));
-    if (e != cudaSuccess) { cudaGetLastError(); delete s; return fail(ctx, KZG_E_NOMEM, "cudaMalloc(bases)"); }
-  }
-  *out = s;
-  return KZG_OK;
-}
-
+// ---- trusted setup ---------------------------------------------------------------------------------------------------
 int32_t kzg_setup_generate(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t first, uint64_t n, kzg_setup** out) {
   if (!ctx || !secret_be || !out) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  kzg_setup* s = nullptr;
-  KZG_TRY(setup_alloc(ctx, n, &s));
-  s->first = first;
-  int32_t st = setup_generate_dev(ctx, secret_be, first, n, s->bases);
-  if (st == KZG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, KZG_E_CUDA, "sync after setup generation");
-  if (st != KZG_OK) { kzg_setup_destroy(s); return st; }
-  *out = s;
+  if (!is_group(ctx)) return one_setup_generate(ctx, secret_be, first, n, out);
+  kzg_setup* S = new_group_setup(ctx, n, choose_layout(ctx, n));
+  S->first = first;
+  int32_t st = for_members(ctx, [&](int g, kzg_ctx* m) {      // index-range sharding: no exchange
+    const uint64_t lo = S->layout == 1 ? S->shard_off[(size_t)g] : 0;
+    const uint64_t cnt = S->layout == 1 ? S->shard_off[(size_t)g + 1] - lo : n;
+    return one_setup_generate(m, secret_be, first + lo, cnt, &S->shards[(size_t)g]);
+  });
+  if (st != KZG_OK) { destroy_group_setup(S); return st; }
+  *out = S;
   return KZG_OK;
 }
 
 int32_t kzg_setup_import_g1(kzg_ctx* ctx, const uint8_t* g1_c48, uint64_t n, kzg_setup** out) {
   if (!ctx || (!g1_c48 && n) || !out) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  kzg_setup* s = nullptr;
-  KZG_TRY(setup_alloc(ctx, n, &s));
-  int32_t st = KZG_OK;
-  if (n) {
-    void* in;
-    st = scratch_get(ctx, SCR_SCALARS, n * 48, &in);
-    if (st == KZG_OK && cudaMemcpyAsync(in, g1_c48, n * 48, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
-      st = fail(ctx, KZG_E_CUDA, "H2D compressed points");
-    int bad = -1;
-    if (st == KZG_OK) st = uncompress_points(ctx, reinterpret_cast<uint8_t*>(in), n, s->bases, &bad);
-    if (st == KZG_OK && bad >= 0) {
-      ctx->err = "Got error while uncompressing: point " + std::to_string(bad);
-      st = KZG_E_BAD_POINT;
-    }
-  }
-  if (st != KZG_OK) { kzg_setup_destroy(s); return st; }
-  *out = s;
+  if (!is_group(ctx)) return one_setup_import_g1(ctx, g1_c48, n, out);
+  kzg_setup* S = new_group_setup(ctx, n, choose_layout(ctx, n));
+  int32_t st = for_members(ctx, [&](int g, kzg_ctx* m) {
+    const uint64_t lo = S->layout == 1 ? S->shard_off[(size_t)g] : 0;
+    const uint64_t cnt = S->layout == 1 ? S->shard_off[(size_t)g + 1] - lo : n;
+    int32_t r = one_setup_import_g1(m, g1_c48 + lo * 48, cnt, &S->shards[(size_t)g]);
+    if (r == KZG_OK) S->shards[(size_t)g]->first = lo;        // position of the shard in the sequence (G2 powers follow it)
+    return r;
+  });
+  if (st != KZG_OK) { destroy_group_setup(S); return st; }
+  *out = S;
   return KZG_OK;
 }
 
 int32_t kzg_setup_export_g1(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count, uint8_t* out_c48) {
-  if (!ctx || !s || first + count > s->n) return fail(ctx, KZG_E_BAD_ARG, "export range outside the setup");
-  if (count == 0) return KZG_OK;
-  DeviceGuard g(ctx->device);
-  void* o;
-  KZG_TRY(scratch_get(ctx, SCR_OUT, count * 48, &o));
-  KZG_TRY(compress_points(ctx, s->bases + first, count, reinterpret_cast<uint8_t*>(o)));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c48, o, count * 48, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_setup_export_g1(ctx, s, first, count, out_c48);
+  if (first > s->n || count > s->n - first) return fail(ctx, KZG_E_BAD_ARG, "export range outside the setup");
+  if (s->layout == 2) return one_setup_export_g1(ctx, s->shards[0], first, count, out_c48);
+  for (int g = 0; g < group_size(ctx); g++) {
+    const uint64_t lo = std::max(first, s->shard_off[(size_t)g]), hi = std::min(first + count, s->shard_off[(size_t)g + 1]);
+    if (lo >= hi) continue;
+    kzg_ctx* m = ctx->members[(size_t)g];
+    int32_t st = one_setup_export_g1(m, s->shards[(size_t)g], lo - s->shard_off[(size_t)g], hi - lo, out_c48 + (lo - first) * 48);
+    if (st != KZG_OK) { if (g) ctx->err = m->err; return st; }
+  }
   return KZG_OK;
 }
 
 uint64_t kzg_setup_len(const kzg_setup* s) { return s ? s->n : 0; }
 
-// ---- G2 half of SetupArtifact (src/trusted_setup.rs:31-35, 64-72) ----------------------------
-static int32_t setup_g2_alloc(kzg_ctx* ctx, kzg_setup* s, uint64_t count) {
-  if (s->g2_c96) { cudaFree(s->g2_c96); s->g2_c96 = nullptr; s->g2_n = 0; }
-  if (count == 0) return KZG_OK;
-  if (cudaMalloc(&s->g2_c96, count * 96) != cudaSuccess) { cudaGetLastError(); return fail(ctx, KZG_E_NOMEM, "cudaMalloc(g2)"); }
-  s->g2_n = count;
-  return KZG_OK;
-}
-
 int32_t kzg_setup_generate_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t secret_be[32], uint64_t count) {
   if (!ctx || !s || !secret_be) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_setup_generate_g2(ctx, s, secret_be, count);
   if (count > s->n) return fail(ctx, KZG_E_BAD_ARG, "more G2 items than setup items");
-  DeviceGuard g(ctx->device);
-  KZG_TRY(setup_g2_alloc(ctx, s, count));
-  KZG_TRY(setup_generate_g2_dev(ctx, secret_be, s->first, count, s->g2_c96));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  return KZG_OK;
+  if (s->layout == 2) return one_setup_generate_g2(ctx, s->shards[0], secret_be, count);
+  return for_members(ctx, [&](int g, kzg_ctx* m) {
+    return one_setup_generate_g2(m, s->shards[(size_t)g], secret_be, shard_share(s, g, count));
+  });
 }
 
 int32_t kzg_setup_import_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t* g2_c96, uint64_t count) {
   if (!ctx || !s || (!g2_c96 && count)) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_setup_import_g2(ctx, s, g2_c96, count);
   if (count > s->n) return fail(ctx, KZG_E_BAD_ARG, "more G2 items than setup items");
-  // Deserialize for G2Point (src/curves.rs:273-343): length fixed by the ABI, blst_p2_uncompress semantics
-  // (flags, coordinates < q, Fq2 square root, on-curve; no subgroup check).  A handful of points (the CLI's setup.json)
-  // is validated on the host; larger sets on the device, one thread per point (a host square root costs ~0.1 ms).
-  DeviceGuard g(ctx->device);
-  const bool on_device = count >= 64;
-  if (!on_device) {
-    for (uint64_t i = 0; i < count; i++) {
-      if (kzg_g2_check(g2_c96 + 96 * i) != KZG_OK) {
-        ctx->err = "Got error while uncompressing: G2 point " + std::to_string(i);
-        return KZG_E_BAD_POINT;
-      }
-    }
-    KZG_TRY(setup_g2_alloc(ctx, s, count));
-    if (count) {
-      KZG_CUDA_OK(ctx, cudaMemcpyAsync(s->g2_c96, g2_c96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
-      KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    return KZG_OK;
-  }
-  void* stage;                                   // validated in scratch first: a rejected import leaves the setup untouched
-  KZG_TRY(scratch_get(ctx, SCR_OUT, count * 96, &stage));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(stage, g2_c96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
-  int64_t bad = -1;
-  KZG_TRY(validate_g2_points(ctx, reinterpret_cast<const uint8_t*>(stage), count, &bad));
-  if (bad >= 0) {
-    ctx->err = "Got error while uncompressing: G2 point " + std::to_string(bad);
-    return KZG_E_BAD_POINT;
-  }
-  KZG_TRY(setup_g2_alloc(ctx, s, count));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(s->g2_c96, stage, count * 96, cudaMemcpyDeviceToDevice, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  return KZG_OK;
+  if (s->layout == 2) return one_setup_import_g2(ctx, s->shards[0], g2_c96, count);
+  return for_members(ctx, [&](int g, kzg_ctx* m) {
+    return one_setup_import_g2(m, s->shards[(size_t)g], g2_c96 + s->shard_off[(size_t)g] * 96, shard_share(s, g, count));
+  });
+}
+
+uint64_t kzg_setup_g2_len(const kzg_setup* s) {
+  if (!s) return 0;
+  if (s->layout == 0) return one_setup_g2_len(s);
+  if (s->layout == 2) return one_setup_g2_len(s->shards[0]);
+  uint64_t c = 0;
+  for (const kzg_setup* sh : s->shards) c += one_setup_g2_len(sh);
+  return c;
 }
 
 int32_t kzg_setup_export_g2(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count, uint8_t* out_c96) {
-  if (!ctx || !s || first + count > s->g2_n) return fail(ctx, KZG_E_BAD_ARG, "export range outside the G2 items");
-  if (count == 0) return KZG_OK;
-  DeviceGuard g(ctx->device);
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c96, s->g2_c96 + first * 96, count * 96, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  return KZG_OK;
-}
-
-uint64_t kzg_setup_g2_len(const kzg_setup* s) { return s ? s->g2_n : 0; }
-
-int32_t kzg_msm_plan(const kzg_ctx* ctx, const kzg_setup* s, uint64_t n, int32_t plan[5]) {
-  if (!ctx || !s || !plan || !s->msm_c) return KZG_E_BAD_ARG;
-  plan[0] = s->msm_c; plan[1] = s->msm_w; plan[2] = 1 << (s->msm_c - 1);
-  plan[3] = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds((uint64_t)s->msm_w * n);
-  plan[4] = (int32_t)MSM_TAB_PITCH;
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_setup_export_g2(ctx, s, first, count, out_c96);
+  if (s->layout == 2) return one_setup_export_g2(ctx, s->shards[0], first, count, out_c96);
+  const uint64_t have = kzg_setup_g2_len(s);
+  if (first > have || count > have - first) return fail(ctx, KZG_E_BAD_ARG, "export range outside the G2 items");
+  for (int g = 0; g < group_size(ctx); g++) {
+    const uint64_t lo = std::max(first, s->shard_off[(size_t)g]), hi = std::min(first + count, s->shard_off[(size_t)g + 1]);
+    if (lo >= hi) continue;
+    kzg_ctx* m = ctx->members[(size_t)g];
+    int32_t st = one_setup_export_g2(m, s->shards[(size_t)g], lo - s->shard_off[(size_t)g], hi - lo, out_c96 + (lo - first) * 96);
+    if (st != KZG_OK) { if (g) ctx->err = m->err; return st; }
+  }
   return KZG_OK;
 }
 
 void kzg_setup_destroy(kzg_setup* s) {
   if (!s) return;
-  DeviceGuard g(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
-  if (s->bases) cudaFree(s->bases);
-  if (s->msm_tab) cudaFree(s->msm_tab);
-  if (s->fix_tab) cudaFree(s->fix_tab);
-  if (s->g2_c96) cudaFree(s->g2_c96);
-  delete s;
+  if (s->layout == 0) one_setup_destroy(s); else destroy_group_setup(s);
 }
 
 int32_t kzg_setup_prepare_msm(kzg_ctx* ctx, kzg_setup* s, int32_t window_bits) {
   if (!ctx || !s) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  return build_msm_table(ctx, s, window_bits);
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_setup_prepare_msm(ctx, s, window_bits);
+  if (s->layout == 2) return one_setup_prepare_msm(ctx, s->shards[0], window_bits);     // single sums run on member 0
+  return for_members(ctx, [&](int g, kzg_ctx* m) { return one_setup_prepare_msm(m, s->shards[(size_t)g], window_bits); });
 }
 
 int32_t kzg_setup_prepare_fixed(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int32_t window_bits) {
   if (!ctx || !s) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  return build_fixed_table(ctx, s, n_points, window_bits);
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_setup_prepare_fixed(ctx, s, n_points, window_bits);
+  if (s->layout != 2)
+    return fail(ctx, KZG_E_BAD_ARG, "fixed-base tables serve blob batches and need a replicated setup (option setup_layout = 2)");
+  return for_members(ctx, [&](int g, kzg_ctx* m) { return one_setup_prepare_fixed(m, s->shards[(size_t)g], n_points, window_bits); });
 }
 
-// ---- single-polynomial operations ----------------------------------------------------------------
-int32_t kzg_msm_g1_partial_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, void* partial_dev) {
-  if (!ctx || !s || !partial_dev) return KZG_E_BAD_ARG;
-  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  DeviceGuard g(ctx->device);
-  return msm_any(ctx, s, reinterpret_cast<const uint8_t*>(scalars_dev), n, reinterpret_cast<G1Xyzz*>(partial_dev));
+int32_t kzg_msm_plan(const kzg_ctx* ctx, const kzg_setup* s, uint64_t n, int32_t plan[5]) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  if (!setup_matches(ctx, s)) return KZG_E_BAD_ARG;
+  if (!is_group(ctx)) return one_msm_plan(ctx, s, n, plan);
+  return one_msm_plan(ctx, s->shards[0], s->layout == 1 ? shard_share(s, 0, n) : n, plan);      // member 0's share
+}
+
+int32_t kzg_setup_fixed_plan(const kzg_setup* s, int64_t plan[4]) {
+  if (!s || !plan) return KZG_E_BAD_ARG;
+  const kzg_setup* one = s->layout == 0 ? s : s->shards[0];
+  if (!one || !one->fix_tab) return KZG_E_BAD_ARG;
+  plan[0] = one->fix_c; plan[1] = one->fix_w; plan[2] = (int64_t)one->fix_n;
+  plan[3] = (int64_t)fixed_table_bytes(one->fix_n, one->fix_c);
+  return KZG_OK;
+}
+
+// ---- one polynomial ----------------------------------------------------------------------------------------------------
+int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, uint8_t out_c48[48]) {
+  if (!ctx || !s || (!scalars_le32 && n) || !out_c48) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_msm_g1(ctx, s, scalars_le32, n, out_c48);
+  return group_msm(ctx, s, scalars_le32, n, true, out_c48);
 }
 
 int32_t kzg_msm_g1_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]) {
-  if (!ctx || !s || !out_c48) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  void* r;
-  KZG_TRY(scratch_get(ctx, SCR_MISC, 1024, &r));
-  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
-  KZG_TRY(kzg_msm_g1_partial_dev(ctx, s, scalars_dev, n, res));
-  KZG_TRY(finish_one(ctx, res, out_c48));
-  update_timers(ctx);
-  return KZG_OK;
-}
-
-int32_t kzg_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, uint8_t out_c48[48]) {
-  if (!ctx || !s || (!scalars_le32 && n) || !out_c48) return KZG_E_BAD_ARG;
-  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  DeviceGuard g(ctx->device);
-  void* d;
-  KZG_TRY(scratch_get(ctx, SCR_SCALARS, n * 32, &d));
-  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, scalars_le32, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return kzg_msm_g1_dev(ctx, s, d, n, out_c48);
-}
-
-// ---- several calls in flight ----------------------------------------------------------------------------------------
-// Ticket t runs on lane t mod L (L = option "lanes", default and at most KZG_MAX_LANES = 4): lane 0 is the context itself,
-// the others are hidden sibling contexts of the same device (own streams, own scratch).  The host->device copy and the
-// bulk kernels of one call overlap the latency-bound phases of the others (the inversion chain of every halving round,
-// the bucket reduction: a few hundred warps for ~0.6 ms); two lanes are worth 13 % at n = 2^20 and 30 % at n = 2^17, four 18 % and 44 %.
-static void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
-  dst->opt_msm_window = src->opt_msm_window; dst->opt_fixed_window = src->opt_fixed_window;
-  dst->opt_reduce_chunk = src->opt_reduce_chunk; dst->opt_heavy_cap = src->opt_heavy_cap; dst->opt_acc_split = src->opt_acc_split;
-  dst->opt_tree_min_rows = src->opt_tree_min_rows; dst->opt_tree_chunk_rows = src->opt_tree_chunk_rows;
-  dst->opt_tree_min_pairs = src->opt_tree_min_pairs; dst->opt_inv_top_fan = src->opt_inv_top_fan; dst->opt_inv_top = src->opt_inv_top;
-  dst->opt_msm_tree_rounds = src->opt_msm_tree_rounds; dst->opt_acc_min_entries = src->opt_acc_min_entries;
-  dst->opt_setup_tree_min = src->opt_setup_tree_min; dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_acc_minblocks = src->opt_acc_minblocks;
-}
-
-static int32_t lane_of(kzg_ctx* ctx, uint32_t ticket, kzg_ctx** lane) {
-  if (!ctx->lanes_in_use) ctx->lanes_in_use = std::min(KZG_MAX_LANES, std::max(1, ctx->opt_lanes));
-  const int l = (int)(ticket % (uint32_t)ctx->lanes_in_use);
-  *lane = ctx;
-  if (l == 0) return KZG_OK;
-  if (!ctx->lane[l]) {
-    int32_t st = kzg_ctx_create(&ctx->lane[l], ctx->device);
-    if (st != KZG_OK) return fail(ctx, st, "could not create another lane of the submission queue");
-  }
-  copy_options(ctx->lane[l], ctx);
-  *lane = ctx->lane[l];
-  return KZG_OK;
-}
-
-// host == true: `scalars` is a host buffer, copied on the lane's copy stream; sharded == true: the result is the
-// fold of every rank's partial (peer exchange), else this context's own sum
-static int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host, bool sharded,
-                             int32_t* ticket) {
-  if (!ctx || !s || (!scalars && n) || !ticket) return KZG_E_BAD_ARG;
-  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  if (sharded && !ctx->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
-  DeviceGuard g(ctx->device);
-  const uint32_t t = ctx->next_ticket;
-  kzg_ctx* lane;
-  KZG_TRY(lane_of(ctx, t, &lane));
-  kzg_ctx::Pending& q = ctx->pending[t % (uint32_t)ctx->lanes_in_use];
-  if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "every lane has a call in flight: wait for the oldest ticket first");
-  if (!s->msm_tab && !(s->fix_tab && n <= s->fix_n)) {      // built once, on the main lane, before any lane reads it
-    KZG_TRY(ensure_msm_table(ctx, s));
-    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  }
-  if (!q.copied) {
-    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.copied, cudaEventDisableTiming));
-    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
-    KZG_CUDA_OK(ctx, cudaMalloc(&q.result, 512));
-    KZG_CUDA_OK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&q.out_host), 64, cudaHostAllocDefault));
-  }
-  const uint8_t* dev_scalars = reinterpret_cast<const uint8_t*>(scalars);
-  if (host) {
-    const size_t bytes = n ? n * 32 : 32;
-    if (q.cap < bytes) {
-      if (q.scalars) { KZG_CUDA_OK(ctx, cudaFree(q.scalars)); q.scalars = nullptr; q.cap = 0; }
-      KZG_CUDA_OK(ctx, cudaMalloc(&q.scalars, bytes));
-      q.cap = bytes;
-    }
-    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.scalars, scalars, n * 32, cudaMemcpyHostToDevice, lane->copy_stream));
-    KZG_CUDA_OK(ctx, cudaEventRecord(q.copied, lane->copy_stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(lane->stream, q.copied, 0));
-    dev_scalars = reinterpret_cast<const uint8_t*>(q.scalars);
-  }
-  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(q.result);
-  uint8_t* out_dev = reinterpret_cast<uint8_t*>(q.result) + 256;
-  lane->throughput_mode = ctx->lanes_in_use > 1;      // several calls in flight: tuned for throughput, not for the shortest chain
-  int32_t st = msm_any(lane, s, dev_scalars, n, res);
-  lane->throughput_mode = false;
-  if (st == KZG_OK) {
-    if (sharded) st = exchange_combine(lane, ctx, t + 1, res, out_dev, reinterpret_cast<uint32_t*>(out_dev + 48));
-    else st = finalize_points(lane, res, 1, out_dev);
-  }
-  if (st != KZG_OK) { if (lane != ctx) ctx->err = lane->err; return st; }
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.out_host, out_dev, 64, cudaMemcpyDeviceToHost, lane->stream));
-  KZG_CUDA_OK(ctx, cudaEventRecord(q.done, lane->stream));
-  q.busy = true; q.sharded = sharded;
-  *ticket = (int32_t)t;
-  ctx->next_ticket = t + 1;
-  return KZG_OK;
+  if (!ctx || !s || (!scalars_dev && n) || !out_c48) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_msm_g1_dev(ctx, s, scalars_dev, n, out_c48);
+  return group_msm(ctx, s, scalars_dev, n, false, out_c48);
 }
 
 int32_t kzg_msm_g1_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket) {
-  return submit_common(ctx, s, scalars_le32, n, true, false, ticket);
+  if (!ctx || !s || (!scalars_le32 && n) || !ticket) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_msm_g1_submit(ctx, s, scalars_le32, n, ticket);
+  return group_msm_submit(ctx, s, scalars_le32, n, true, ticket);
 }
+
 int32_t kzg_msm_g1_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket) {
-  return submit_common(ctx, s, scalars_dev, n, false, false, ticket);
-}
-int32_t kzg_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket) {
-  return submit_common(ctx, s, scalars_dev, n, false, true, ticket);
-}
-int32_t kzg_msm_g1_sharded_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket) {
-  return submit_common(ctx, s, scalars_le32, n, true, true, ticket);
+  if (!ctx || !s || (!scalars_dev && n) || !ticket) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_msm_g1_submit_dev(ctx, s, scalars_dev, n, ticket);
+  return group_msm_submit(ctx, s, scalars_dev, n, false, ticket);
 }
 
 int32_t kzg_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
-  if (!ctx || !out_c48 || ticket < 0) return KZG_E_BAD_ARG;
-  const uint32_t t = (uint32_t)ticket, L = (uint32_t)std::max(1, ctx->lanes_in_use);
-  kzg_ctx::Pending& q = ctx->pending[t % L];
-  if (!q.busy || ctx->next_ticket - t < 1 || ctx->next_ticket - t > L)
-    return fail(ctx, KZG_E_BAD_ARG, "no call in flight under this ticket");
-  DeviceGuard g(ctx->device);
-  KZG_CUDA_OK(ctx, cudaEventSynchronize(q.done));
-  q.busy = false;
-  if (q.sharded) {
-    uint32_t st;
-    memcpy(&st, q.out_host + 48, 4);
-    if (st != 0) return fail(ctx, KZG_E_CUDA, "peer exchange timed out: a rank did not publish its partial sum");
-  }
-  memcpy(out_c48, q.out_host, 48);
-  return KZG_OK;
-}
-
-// ---- multi-GPU exchange over peer memory ---------------------------------------------------------------------------
-int32_t kzg_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_out[KZG_P2P_HANDLE_BYTES]) {
-  if (!ctx || !handle_out || world < 1 || world > KZG_MAX_PEERS || rank < 0 || rank >= world) return KZG_E_BAD_ARG;
-  static_assert(sizeof(cudaIpcMemHandle_t) == KZG_P2P_HANDLE_BYTES, "IPC handle size");
-  DeviceGuard g(ctx->device);
-  if (ctx->p2p_box[ctx->p2p_rank] && ctx->p2p_world) return fail(ctx, KZG_E_BAD_ARG, "peer exchange already initialised on this context");
-  void* box = nullptr;
-  KZG_CUDA_OK(ctx, cudaMalloc(&box, sizeof(PeerMailbox)));
-  KZG_CUDA_OK(ctx, cudaMemset(box, 0, sizeof(PeerMailbox)));
-  KZG_CUDA_OK(ctx, cudaDeviceSynchronize());
-  cudaIpcMemHandle_t h;
-  KZG_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, box));
-  memcpy(handle_out, &h, sizeof(h));
-  ctx->p2p_world = world; ctx->p2p_rank = rank; ctx->p2p_box[rank] = box; ctx->p2p_connected = false;
-  return KZG_OK;
-}
-
-int32_t kzg_p2p_connect(kzg_ctx* ctx, const uint8_t* handles) {
-  if (!ctx || !handles || ctx->p2p_world < 1 || !ctx->p2p_box[ctx->p2p_rank]) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  for (int r = 0; r < ctx->p2p_world; r++) {
-    if (r == ctx->p2p_rank) continue;
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handles + (size_t)r * KZG_P2P_HANDLE_BYTES, sizeof(h));
-    KZG_CUDA_OK(ctx, cudaIpcOpenMemHandle(&ctx->p2p_box[r], h, cudaIpcMemLazyEnablePeerAccess));
-  }
-  ctx->p2p_connected = true;
-  return KZG_OK;
-}
-
-int32_t kzg_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]) {
-  if (!ctx || !s || !out_c48) return KZG_E_BAD_ARG;
-  int32_t t = -1;
-  KZG_TRY(kzg_msm_g1_sharded_submit_dev(ctx, s, scalars_dev, n, &t));
-  return kzg_msm_g1_wait(ctx, t, out_c48);
-}
-
-int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count, uint8_t out_c48[48]) {
-  if (!ctx || (!partials_dev && count) || !out_c48) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  void* r;
-  KZG_TRY(scratch_get(ctx, SCR_MISC, 1024, &r));
-  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
-  KZG_TRY(sum_points(ctx, reinterpret_cast<const G1Xyzz*>(partials_dev), count, res));
-  return finish_one(ctx, res, out_c48);
+  if (!ctx || !out_c48) return KZG_E_BAD_ARG;
+  if (!is_group(ctx)) return one_msm_g1_wait(ctx, ticket, out_c48);
+  return group_msm_wait(ctx, ticket, out_c48);
 }
 
 int32_t kzg_commit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n, uint8_t out_c48[48]) {
   if (!ctx || !s || (!coeffs_le32 && n) || !out_c48) return KZG_E_BAD_ARG;
-  uint64_t nt = trimmed_len(coeffs_le32, n);
-  // (degree() + 1) > setup.len()  with degree() == 0 for the empty / zero polynomial (src/polynomial.rs:95-100,201)
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_commit(ctx, s, coeffs_le32, n, out_c48);
+  const uint64_t nt = trimmed_len_host(coeffs_le32, n);
+  // (degree() + 1) > setup.len(), degree() == 0 for the empty / zero polynomial (src/polynomial.rs:95-100, 201)
   if (std::max<uint64_t>(nt, 1) > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  return kzg_msm_g1(ctx, s, coeffs_le32, nt, out_c48);
-}
-
-int32_t kzg_evaluate_dev(kzg_ctx* ctx, const void* coeffs_dev, uint64_t n, const uint8_t z_le[32], uint8_t y_le[32]) {
-  if (!ctx || (!coeffs_dev && n) || !z_le || !y_le) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  void* m;
-  KZG_TRY(scratch_get(ctx, SCR_FR_B, 256, &m));
-  uint8_t* zd = reinterpret_cast<uint8_t*>(m);
-  uint8_t* yd = zd + 64;
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le, 32, cudaMemcpyHostToDevice, ctx->stream));
-  KZG_TRY(poly_eval_quotient(ctx, reinterpret_cast<const uint8_t*>(coeffs_dev), 1, n, zd, yd, nullptr));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le, yd, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  return KZG_OK;
+  return group_msm(ctx, s, coeffs_le32, nt, true, out_c48);
 }
 
 int32_t kzg_evaluate(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], uint8_t y_le[32]) {
-  if (!ctx || (!coeffs_le32 && n) || !z_le || !y_le) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  void* d;
-  KZG_TRY(scratch_get(ctx, SCR_SCALARS, n * 32, &d));
-  if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  return kzg_evaluate_dev(ctx, d, n, z_le, y_le);
+  return one_evaluate(ctx, coeffs_le32, n, z_le, y_le);          // group: member 0 (one polynomial does not shard)
 }
 
-// shared by kzg_quotient / kzg_open: stages coefficients, runs the scan, applies the reference's
-// divide_by_root error rules.  On success *q_dev holds nt-1 (or 0) canonical coefficients.
-static int32_t quotient_core(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
-                             const uint8_t* y_le, uint8_t y_out[32], uint8_t** q_dev, uint64_t* q_len) {
-  uint64_t nt = trimmed_len(coeffs_le32, n);
-  void *d, *m, *q;
-  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(nt, 1) * 32, &d));
-  KZG_TRY(scratch_get(ctx, SCR_QUOT, std::max<uint64_t>(nt, 1) * 32, &q));
-  KZG_TRY(scratch_get(ctx, SCR_FR_B, 256, &m));
-  uint8_t* zd = reinterpret_cast<uint8_t*>(m);
-  uint8_t* yd = zd + 64;
-  if (nt) KZG_CUDA_OK(ctx, cudaMemcpyAsync(d, coeffs_le32, nt * 32, cudaMemcpyHostToDevice, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le, 32, cudaMemcpyHostToDevice, ctx->stream));
-  KZG_TRY(poly_eval_quotient(ctx, reinterpret_cast<uint8_t*>(d), 1, nt, zd, yd, reinterpret_cast<uint8_t*>(q)));
-  uint8_t y_dev_val[32];
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_dev_val, yd, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (y_out) memcpy(y_out, y_dev_val, 32);
-  bool y_matches = true;
-  if (y_le) {
-    uint8_t yr[32];
-    kzg_fr_reduce(y_le, yr);
-    y_matches = memcmp(yr, y_dev_val, 32) == 0;
-  }
-  if (nt <= 1) {
-    // p - y is a constant: zero -> empty quotient, otherwise "Unable to divide a constant polynomial"
-    if (!y_matches) return fail(ctx, KZG_E_CONSTANT_POLY, kzg_status_string(KZG_E_CONSTANT_POLY));
-    *q_len = 0;
-  } else {
-    if (!y_matches) return fail(ctx, KZG_E_REMAINDER_NONZERO, kzg_status_string(KZG_E_REMAINDER_NONZERO));
-    *q_len = nt - 1;
-  }
-  *q_dev = reinterpret_cast<uint8_t*>(q);
-  return KZG_OK;
+int32_t kzg_evaluate_dev(kzg_ctx* ctx, const void* coeffs_dev, uint64_t n, const uint8_t z_le[32], uint8_t y_le[32]) {
+  return one_evaluate_dev(ctx, coeffs_dev, n, z_le, y_le);
 }
 
-int32_t kzg_quotient(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
-                     const uint8_t* y_le, uint8_t* q_le32, uint64_t* q_len) {
-  if (!ctx || (!coeffs_le32 && n) || !z_le || !q_len) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  uint8_t* qd = nullptr;
-  KZG_TRY(quotient_core(ctx, coeffs_le32, n, z_le, y_le, nullptr, &qd, q_len));
-  if (*q_len && q_le32) {
-    KZG_CUDA_OK(ctx, cudaMemcpyAsync(q_le32, qd, *q_len * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  }
-  return KZG_OK;
+int32_t kzg_quotient(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], const uint8_t* y_le,
+                     uint8_t* q_le32, uint64_t* q_len) {
+  return one_quotient(ctx, coeffs_le32, n, z_le, y_le, q_le32, q_len);
 }
 
 int32_t kzg_open(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32],
                  const uint8_t* y_expected_le, uint8_t y_out_le[32], uint8_t proof_c48[48]) {
   if (!ctx || !s || (!coeffs_le32 && n) || !z_le || !proof_c48) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_open(ctx, s, coeffs_le32, n, z_le, y_expected_le, y_out_le, proof_c48);
+  // the quotient scan on member 0, then the sum over every member's range: the members read their slice of the
+  // quotient straight out of member 0's memory (it stays put until the wait below)
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ctx->device);
   uint8_t* qd = nullptr;
   uint64_t ql = 0;
-  KZG_TRY(quotient_core(ctx, coeffs_le32, n, z_le, y_expected_le, y_out_le, &qd, &ql));
+  int32_t st = quotient_core(ctx, coeffs_le32, n, z_le, y_expected_le, y_out_le, &qd, &ql);
+  cudaSetDevice(prev);
+  KZG_TRY(st);
   if (std::max<uint64_t>(ql, 1) > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  return kzg_msm_g1_dev(ctx, s, qd, ql, proof_c48);
+  return group_msm(ctx, s, qd, ql, false, proof_c48);
 }
 
-// ---- blob batches ------------------------------------------------------------------------------------
-// lane l >= 1 of a context (hidden sibling context: own streams and scratch), created on first use
-static int32_t sibling_lane(kzg_ctx* ctx, int l, kzg_ctx** lane) {
-  if (l < 1 || l >= KZG_MAX_LANES) return KZG_E_BAD_ARG;
-  if (!ctx->lane[l]) {
-    int32_t st = kzg_ctx_create(&ctx->lane[l], ctx->device);
-    if (st != KZG_OK) return fail(ctx, st, "could not create another lane of the context");
-  }
-  copy_options(ctx->lane[l], ctx);
-  *lane = ctx->lane[l];
-  return KZG_OK;
+// ---- one process per GPU: exchange over CUDA IPC mailboxes ----------------------------------------------------------------
+#define KZG_NOT_ON_GROUP(ctx)                                                                                                  \
+  do {                                                                                                                         \
+    if (is_group(ctx))                                                                                                         \
+      return fail(ctx, KZG_E_BAD_ARG, "a multi-device context shards internally: use the plain call (kzg_msm_g1, kzg_commit ...)"); \
+  } while (0)
+
+int32_t kzg_msm_g1_partial_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, void* partial_dev) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_NOT_ON_GROUP(ctx);
+  KZG_CHECK_SETUP(ctx, s);
+  return one_msm_g1_partial_dev(ctx, s, scalars_dev, n, partial_dev);
+}
+int32_t kzg_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_out[KZG_P2P_HANDLE_BYTES]) {
+  if (!ctx) return KZG_E_BAD_ARG;
+  KZG_NOT_ON_GROUP(ctx);
+  return one_p2p_init(ctx, world, rank, handle_out);
+}
+int32_t kzg_p2p_connect(kzg_ctx* ctx, const uint8_t* handles) {
+  if (!ctx) return KZG_E_BAD_ARG;
+  KZG_NOT_ON_GROUP(ctx);
+  return one_p2p_connect(ctx, handles);
+}
+int32_t kzg_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_NOT_ON_GROUP(ctx);
+  KZG_CHECK_SETUP(ctx, s);
+  return one_msm_g1_sharded_dev(ctx, s, scalars_dev, n, out_c48);
+}
+int32_t kzg_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_NOT_ON_GROUP(ctx);
+  KZG_CHECK_SETUP(ctx, s);
+  return one_msm_g1_sharded_submit_dev(ctx, s, scalars_dev, n, ticket);
+}
+int32_t kzg_msm_g1_sharded_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_NOT_ON_GROUP(ctx);
+  KZG_CHECK_SETUP(ctx, s);
+  return one_msm_g1_sharded_submit(ctx, s, scalars_le32, n, ticket);
+}
+int32_t kzg_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count, uint8_t out_c48[48]) {
+  return one_g1_combine_dev(ctx, partials_dev, count, out_c48);
 }
 
-static int32_t batch_points_out(kzg_ctx* ctx, const G1Xyzz* pts, uint64_t blobs, uint8_t* out_c48_dev) {
-  void* aff;
-  KZG_TRY(scratch_get(ctx, SCR_BATCH_AFF, blobs * sizeof(G1Affine), &aff));
-  KZG_TRY(batch_to_affine(ctx, pts, blobs, reinterpret_cast<G1Affine*>(aff)));
-  return compress_points(ctx, reinterpret_cast<G1Affine*>(aff), blobs, out_c48_dev);
-}
-
-static int32_t msm_batch_any(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t blobs, uint64_t n,
-                             uint64_t stride, G1Xyzz* out) {
-  if (s->fix_tab && n <= s->fix_n) return msm_fixed_batch(ctx, s, scalars_dev, blobs, n, stride, out);
-  KZG_TRY(ensure_msm_table(ctx, s));
-  for (uint64_t b = 0; b < blobs; b++) KZG_TRY(msm_bucket(ctx, s, scalars_dev + b * stride * 32, n, out + b));
-  return KZG_OK;
-}
-
-int32_t kzg_commit_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n,
-                             void* out_c48_dev) {
-  if (!ctx || !s || (!coeffs_dev && blobs * n) || !out_c48_dev) return KZG_E_BAD_ARG;
-  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  if (blobs == 0) return KZG_OK;
-  DeviceGuard g(ctx->device);
-  void* pts;
-  KZG_TRY(scratch_get(ctx, SCR_BATCH_PTS, blobs * sizeof(G1Xyzz), &pts));
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-  KZG_TRY(msm_batch_any(ctx, s, reinterpret_cast<const uint8_t*>(coeffs_dev), blobs, n, n, reinterpret_cast<G1Xyzz*>(pts)));
-  KZG_TRY(batch_points_out(ctx, reinterpret_cast<G1Xyzz*>(pts), blobs, reinterpret_cast<uint8_t*>(out_c48_dev)));
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-  return KZG_OK;
-}
-
-int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n,
-                           const void* z_dev, void* y_dev, void* proofs_c48_dev) {
-  if (!ctx || !s || (!coeffs_dev && blobs * n) || !z_dev || !y_dev || !proofs_c48_dev) return KZG_E_BAD_ARG;
-  if (n > s->n + 1) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  if (blobs == 0) return KZG_OK;
-  DeviceGuard g(ctx->device);
-  void *pts, *q;
-  KZG_TRY(scratch_get(ctx, SCR_BATCH_PTS, blobs * sizeof(G1Xyzz), &pts));
-  KZG_TRY(scratch_get(ctx, SCR_QUOT, std::max<uint64_t>(blobs * n, 1) * 32, &q));
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-  KZG_TRY(poly_eval_quotient(ctx, reinterpret_cast<const uint8_t*>(coeffs_dev), blobs, n, reinterpret_cast<const uint8_t*>(z_dev),
-                             reinterpret_cast<uint8_t*>(y_dev), reinterpret_cast<uint8_t*>(q)));
-  uint64_t nq = n ? n - 1 : 0;
-  KZG_TRY(msm_batch_any(ctx, s, reinterpret_cast<uint8_t*>(q), blobs, nq, n, reinterpret_cast<G1Xyzz*>(pts)));
-  KZG_TRY(batch_points_out(ctx, reinterpret_cast<G1Xyzz*>(pts), blobs, reinterpret_cast<uint8_t*>(proofs_c48_dev)));
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-  return KZG_OK;
-}
-
-// commit + open of the same rows: two independent MSM batches, the commitments on the context's own lane and the
-// proofs (quotient scan + MSM) on a sibling lane, so that the latency-bound inversion chains of one tree (3 small
-// launches per round, ~9 % of a batch) run under the bulk kernels of the other.  Inputs must be ready on ctx->stream;
-// on return ctx->stream has joined the sibling lane.
-int32_t kzg_commit_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n,
-                                  const void* z_dev, void* commits_c48_dev, void* y_dev, void* proofs_c48_dev) {
-  if (!ctx || !s || (!coeffs_dev && blobs * n) || !z_dev || !commits_c48_dev || !y_dev || !proofs_c48_dev) return KZG_E_BAD_ARG;
-  if (blobs == 0) return KZG_OK;
-  DeviceGuard g(ctx->device);
-  kzg_ctx* side = ctx;
-  if (ctx->opt_lanes > 1) KZG_TRY(sibling_lane(ctx, 1, &side));
-  if (side != ctx) {
-    KZG_CUDA_OK(ctx, cudaEventRecord(side->ev_copy[0], ctx->stream));          // inputs (and earlier users of the outputs) done
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(side->stream, side->ev_copy[0], 0));
-  }
-  int32_t st = kzg_open_batch_dev(side, s, coeffs_dev, blobs, n, z_dev, y_dev, proofs_c48_dev);
-  if (st != KZG_OK) { if (side != ctx) ctx->err = side->err; return st; }
-  KZG_TRY(kzg_commit_batch_dev(ctx, s, coeffs_dev, blobs, n, commits_c48_dev));
-  if (side != ctx) {
-    KZG_CUDA_OK(ctx, cudaEventRecord(side->ev_copy[1], side->stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, side->ev_copy[1], 0));
-  }
-  return KZG_OK;
-}
-
-// rows per host->device staging chunk of a batch call: the tree path's chunk for large batches, else everything
-static uint64_t batch_chunk_rows(const kzg_ctx* ctx, uint64_t blobs) {
-  const uint64_t c = ctx->opt_tree_chunk_rows > 0 ? (uint64_t)ctx->opt_tree_chunk_rows : 2048;
-  return (blobs >= 2 * c && blobs >= (uint64_t)ctx->opt_tree_min_rows) ? c : blobs;
-}
-
-// The first staging chunk is an eighth of the others: its copy is the only one that nothing hides (2048 rows of 4096
-// coefficients = 256 MiB, ~10 ms), and its kernels then cover the copy of the first full chunk.
-static uint64_t first_chunk_rows(uint64_t chunk, uint64_t blobs, uint64_t r0) {
-  return (r0 == 0 && blobs > chunk && chunk >= 64) ? chunk / 8 : chunk;
-}
-
-static uint64_t batch_max_trimmed(const uint8_t* coeffs, uint64_t blobs, uint64_t n) {
-  uint64_t m = 0;
-  for (uint64_t b = 0; b < blobs; b++) m = std::max(m, trimmed_len(coeffs + b * n * 32, n));
-  return m;
-}
-
-int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n,
-                         uint8_t* out_c48) {
+// ---- blob batches ------------------------------------------------------------------------------------------------------
+// Group, replicated setup: rows split by member, no exchange.  Group, range-sharded setup (polynomials too long to
+// replicate): row after row through the sharded sum.
+int32_t kzg_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n, uint8_t* out_c48) {
   if (!ctx || !s || (!coeffs_le32 && blobs * n) || !out_c48) return KZG_E_BAD_ARG;
-  if (blobs == 0) return KZG_OK;
-  if (std::max<uint64_t>(n, 1) > s->n && std::max<uint64_t>(batch_max_trimmed(coeffs_le32, blobs, n), 1) > s->n)
-    return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  if (n > s->n) return fail(ctx, KZG_E_BAD_ARG, "batch with trailing-zero padding beyond the setup is not supported");
-  DeviceGuard g(ctx->device);
-  void *d, *o;
-  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(blobs * n, 1) * 32, &d));
-  KZG_TRY(scratch_get(ctx, SCR_OUT, blobs * 48, &o));
-  // chunks of rows: the copy of chunk k+1 (copy stream) overlaps the reduction of chunk k (main stream)
-  const uint64_t chunk = batch_chunk_rows(ctx, blobs);
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));          // scratch of earlier calls is free
-  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
-  uint64_t k = 0;
-  for (uint64_t r0 = 0, rows = 0; r0 < blobs; r0 += rows, k++) {
-    rows = std::min(first_chunk_rows(chunk, blobs, r0), blobs - r0);
-    uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
-    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k % 7], 0));
-    KZG_TRY(kzg_commit_batch_dev(ctx, s, dc, rows, n, reinterpret_cast<uint8_t*>(o) + r0 * 48));
-  }
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(out_c48, o, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  update_timers(ctx);
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_commit_batch(ctx, s, coeffs_le32, blobs, n, out_c48);
+  if (s->layout == 2)
+    return group_rows(ctx, blobs, [&](int g, kzg_ctx* m, uint64_t r0, uint64_t rows) {
+      return one_commit_batch(m, s->shards[(size_t)g], coeffs_le32 + r0 * n * 32, rows, n, out_c48 + r0 * 48);
+    });
+  for (uint64_t b = 0; b < blobs; b++) KZG_TRY(kzg_commit(ctx, s, coeffs_le32 + b * n * 32, n, out_c48 + b * 48));
   return KZG_OK;
 }
 
 int32_t kzg_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n,
                        const uint8_t* z_le32, uint8_t* y_le32, uint8_t* proofs_c48) {
   if (!ctx || !s || (!coeffs_le32 && blobs * n) || !z_le32 || !y_le32 || !proofs_c48) return KZG_E_BAD_ARG;
-  if (blobs == 0) return KZG_OK;
-  DeviceGuard g(ctx->device);
-  void *d, *o, *zy;
-  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(blobs * n, 1) * 32, &d));
-  KZG_TRY(scratch_get(ctx, SCR_OUT, blobs * 48, &o));
-  KZG_TRY(scratch_get(ctx, SCR_FR_A, blobs * 64, &zy));
-  uint8_t* zd = reinterpret_cast<uint8_t*>(zy);
-  uint8_t* yd = zd + blobs * 32;
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le32, blobs * 32, cudaMemcpyHostToDevice, ctx->stream));
-  const uint64_t chunk = batch_chunk_rows(ctx, blobs);
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
-  uint64_t k = 0;
-  for (uint64_t r0 = 0, rows = 0; r0 < blobs; r0 += rows, k++) {
-    rows = std::min(first_chunk_rows(chunk, blobs, r0), blobs - r0);
-    uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
-    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k % 7], 0));
-    KZG_TRY(kzg_open_batch_dev(ctx, s, dc, rows, n, zd + r0 * 32, yd + r0 * 32, reinterpret_cast<uint8_t*>(o) + r0 * 48));
-  }
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le32, yd, blobs * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(proofs_c48, o, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  update_timers(ctx);
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_open_batch(ctx, s, coeffs_le32, blobs, n, z_le32, y_le32, proofs_c48);
+  if (s->layout == 2)
+    return group_rows(ctx, blobs, [&](int g, kzg_ctx* m, uint64_t r0, uint64_t rows) {
+      return one_open_batch(m, s->shards[(size_t)g], coeffs_le32 + r0 * n * 32, rows, n, z_le32 + r0 * 32, y_le32 + r0 * 32,
+                            proofs_c48 + r0 * 48);
+    });
+  for (uint64_t b = 0; b < blobs; b++)
+    KZG_TRY(kzg_open(ctx, s, coeffs_le32 + b * n * 32, n, z_le32 + b * 32, nullptr, y_le32 + b * 32, proofs_c48 + b * 48));
   return KZG_OK;
 }
 
-// commit + open of every blob with ONE host->device pass over the coefficients (kzg_commit_batch followed by
-// kzg_open_batch copies them twice): chunk k+1 is staged on the copy stream while chunk k is committed and opened
 int32_t kzg_commit_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n,
                               const uint8_t* z_le32, uint8_t* commits_c48, uint8_t* y_le32, uint8_t* proofs_c48) {
   if (!ctx || !s || (!coeffs_le32 && blobs * n) || !z_le32 || !commits_c48 || !y_le32 || !proofs_c48) return KZG_E_BAD_ARG;
-  if (blobs == 0) return KZG_OK;
-  if (std::max<uint64_t>(n, 1) > s->n && std::max<uint64_t>(batch_max_trimmed(coeffs_le32, blobs, n), 1) > s->n)
-    return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
-  if (n > s->n) return fail(ctx, KZG_E_BAD_ARG, "batch with trailing-zero padding beyond the setup is not supported");
-  DeviceGuard g(ctx->device);
-  void *d, *o, *zy;
-  KZG_TRY(scratch_get(ctx, SCR_SCALARS, std::max<uint64_t>(blobs * n, 1) * 32, &d));
-  KZG_TRY(scratch_get(ctx, SCR_OUT, blobs * 96, &o));
-  KZG_TRY(scratch_get(ctx, SCR_FR_A, blobs * 64, &zy));
-  uint8_t* cd = reinterpret_cast<uint8_t*>(o);
-  uint8_t* pd = cd + blobs * 48;
-  uint8_t* zd = reinterpret_cast<uint8_t*>(zy);
-  uint8_t* yd = zd + blobs * 32;
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(zd, z_le32, blobs * 32, cudaMemcpyHostToDevice, ctx->stream));
-  const uint64_t chunk = batch_chunk_rows(ctx, blobs);
-  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[7], ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[7], 0));
-  uint64_t k = 0;
-  for (uint64_t r0 = 0, rows = 0; r0 < blobs; r0 += rows, k++) {
-    rows = std::min(first_chunk_rows(chunk, blobs, r0), blobs - r0);
-    uint8_t* dc = reinterpret_cast<uint8_t*>(d) + r0 * n * 32;
-    if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(dc, coeffs_le32 + r0 * n * 32, rows * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[k % 7], ctx->copy_stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[k % 7], 0));
-    KZG_TRY(kzg_commit_open_batch_dev(ctx, s, dc, rows, n, zd + r0 * 32, cd + r0 * 48, yd + r0 * 32, pd + r0 * 48));
-  }
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(commits_c48, cd, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(y_le32, yd, blobs * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(proofs_c48, pd, blobs * 48, cudaMemcpyDeviceToHost, ctx->stream));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  update_timers(ctx);
-  return KZG_OK;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_commit_open_batch(ctx, s, coeffs_le32, blobs, n, z_le32, commits_c48, y_le32, proofs_c48);
+  if (s->layout == 2)
+    return group_rows(ctx, blobs, [&](int g, kzg_ctx* m, uint64_t r0, uint64_t rows) {
+      return one_commit_open_batch(m, s->shards[(size_t)g], coeffs_le32 + r0 * n * 32, rows, n, z_le32 + r0 * 32,
+                                   commits_c48 + r0 * 48, y_le32 + r0 * 32, proofs_c48 + r0 * 48);
+    });
+  KZG_TRY(kzg_commit_batch(ctx, s, coeffs_le32, blobs, n, commits_c48));
+  return kzg_open_batch(ctx, s, coeffs_le32, blobs, n, z_le32, y_le32, proofs_c48);
 }
 
-// ---- diagnostics ---------------------------------------------------------------------------------------
-int32_t kzg_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s) {
-  if (!ctx || !wide_mac_per_s) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  return probe_imad(ctx, wide_mac_per_s);
+// device-resident rows (anywhere the members can reach); results are queued, kzg_ctx_sync waits for every member
+int32_t kzg_commit_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n, void* out_c48_dev) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_commit_batch_dev(ctx, s, coeffs_dev, blobs, n, out_c48_dev);
+  if (s->layout != 2) return fail(ctx, KZG_E_BAD_ARG, "device-resident batches on a multi-device context need a replicated setup");
+  return group_rows(ctx, blobs, [&](int g, kzg_ctx* m, uint64_t r0, uint64_t rows) {
+    return one_commit_batch_dev(m, s->shards[(size_t)g], cu8(coeffs_dev) + r0 * n * 32, rows, n, u8(out_c48_dev) + r0 * 48);
+  });
 }
 
-int32_t kzg_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s) {
-  if (!ctx || !fq_mul_per_s) return KZG_E_BAD_ARG;
-  DeviceGuard g(ctx->device);
-  return probe_fq_mul(ctx, fq_mul_per_s);
+int32_t kzg_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n, const void* z_dev,
+                           void* y_dev, void* proofs_c48_dev) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_open_batch_dev(ctx, s, coeffs_dev, blobs, n, z_dev, y_dev, proofs_c48_dev);
+  if (s->layout != 2) return fail(ctx, KZG_E_BAD_ARG, "device-resident batches on a multi-device context need a replicated setup");
+  return group_rows(ctx, blobs, [&](int g, kzg_ctx* m, uint64_t r0, uint64_t rows) {
+    return one_open_batch_dev(m, s->shards[(size_t)g], cu8(coeffs_dev) + r0 * n * 32, rows, n, cu8(z_dev) + r0 * 32,
+                              u8(y_dev) + r0 * 32, u8(proofs_c48_dev) + r0 * 48);
+  });
 }
+
+int32_t kzg_commit_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n,
+                                  const void* z_dev, void* commits_c48_dev, void* y_dev, void* proofs_c48_dev) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  KZG_CHECK_SETUP(ctx, s);
+  if (!is_group(ctx)) return one_commit_open_batch_dev(ctx, s, coeffs_dev, blobs, n, z_dev, commits_c48_dev, y_dev, proofs_c48_dev);
+  if (s->layout != 2) return fail(ctx, KZG_E_BAD_ARG, "device-resident batches on a multi-device context need a replicated setup");
+  return group_rows(ctx, blobs, [&](int g, kzg_ctx* m, uint64_t r0, uint64_t rows) {
+    return one_commit_open_batch_dev(m, s->shards[(size_t)g], cu8(coeffs_dev) + r0 * n * 32, rows, n, cu8(z_dev) + r0 * 32,
+                                     u8(commits_c48_dev) + r0 * 48, u8(y_dev) + r0 * 32, u8(proofs_c48_dev) + r0 * 48);
+  });
+}
+
+// ---- diagnostics (member 0 of a group) -----------------------------------------------------------------------------------
+int32_t kzg_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s) { return one_probe_imad_peak(ctx, wide_mac_per_s); }
+int32_t kzg_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s) { return one_probe_fq_mul(ctx, fq_mul_per_s); }
 
 }  // extern "C"

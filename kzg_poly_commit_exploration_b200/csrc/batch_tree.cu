@@ -318,7 +318,9 @@ int32_t msm_fixed_batch_tree(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* sc
     KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
     G1Affine* cur = reinterpret_cast<G1Affine*>(A);
     G1Affine* nxt = reinterpret_cast<G1Affine*>(B);
+    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));      // the dominant kernel of a blob batch (kzg_ctx_last_kernel_ms(2))
     k_r1_add<<<blocks_for(T, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, n, stride_scalars, s->fix_tab, c, W, prefix, tot, cur);
+    KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
     KZG_LAUNCHED(ctx);
     uint64_t L = n * KP;
     // generic rounds while there is enough independent work to hide the inversion latency

@@ -45,7 +45,8 @@ struct kzg_ctx {
   kzg::G1Affine* gtable = nullptr;     // [16][32768] multiples of the generator (setup generation)
   void* g2table = nullptr;             // [20][4096] signed-window multiples of the G2 generator (setup_g2.cu)
   int opt_msm_window = 0;              // 0 = auto
-  int opt_fixed_window = 0;            // 0 = auto
+  int opt_fixed_window = 0;            // 0 = auto: the widest window whose table fits the memory budget (setup.cu auto_fixed_window)
+  int64_t opt_fixed_table_max_bytes = 0;   // budget of that choice; 0 = 60 % of the device memory free at the time
   int opt_reduce_chunk = 16;
   int opt_heavy_cap = 1024;
   int opt_acc_split = -1;              // log2(threads per bucket), -1 = auto
@@ -85,8 +86,20 @@ struct kzg_ctx {
   // multi-GPU exchange over peer memory (msm_tail.cu k_exchange_combine): box[r] = rank r's mailbox as seen from here
   int p2p_world = 0, p2p_rank = 0;
   bool p2p_connected = false;
+  bool p2p_ipc = true;                 // peers' mailboxes are CUDA IPC mappings (one process per GPU); false: plain peer pointers
+  bool p2p_failed = false;             // a collective call timed out or was abandoned: the sequence numbers are out of step for good
+  uint32_t p2p_seq = 0;                // number of the last collective (sharded) call issued on this context
   void* p2p_box[kzg::KZG_MAX_PEERS] = {};
-  long long p2p_timeout_cycles = 1ll << 32;      // ~2 s of spinning before a missing peer becomes an error
+  int sm_clock_khz = 1965000;          // cudaDevAttrClockRate: clock64() ticks per ms, for the exchange timeout
+  long long p2p_timeout_cycles = 20000ll * 1965000;   // spinning time before a missing peer becomes an error (20 s; option p2p_timeout_ms)
+  int last_lane = 0;                   // lane the most recent bulk call ran on (its events feed kzg_ctx_last_kernel_ms)
+  // single-process multi-GPU (kzg_ctx_create_multi, abi.cu): this context is the head of a GROUP of per-device member
+  // contexts; members[0] == this.  Every member has a host worker thread that issues its launches, so that one caller
+  // drives all devices in parallel.  Empty for a plain single-device context.
+  std::vector<kzg_ctx*> members;
+  kzg_ctx* group_head = nullptr;       // set on every member (also on the head itself) of a group
+  void* group_state = nullptr;         // abi.cu: worker threads, group tickets (owned by the head)
+  int opt_setup_layout = 0;            // group setups: 0 = auto (replicate up to 2^16 points, else shard by point range), 1 = range, 2 = replicated
 };
 
 struct kzg_setup {
@@ -106,6 +119,11 @@ struct kzg_setup {
   int fix_c = 0, fix_w = 0;
   uint64_t fix_n = 0;
   kzg::G1Affine* fix_tab = nullptr;
+  // setup of a multi-device context: one per-device setup per member.  layout 1: shard g holds the contiguous point range
+  // [shard_off[g], shard_off[g+1]) of the n items (bases == nullptr here); layout 2: every shard holds all n items.
+  int layout = 0;
+  std::vector<kzg_setup*> shards;
+  std::vector<uint64_t> shard_off;
 };
 
 namespace kzg {
@@ -162,6 +180,8 @@ int32_t compress_points(kzg_ctx* ctx, const G1Affine* in_dev, uint64_t n, uint8_
 int32_t uncompress_points(kzg_ctx* ctx, const uint8_t* in_dev, uint64_t n, G1Affine* out_dev, int* bad_index);
 int32_t build_msm_table(kzg_ctx* ctx, kzg_setup* s, int c);
 int32_t build_fixed_table(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int c);
+uint64_t fixed_table_bytes(uint64_t n_points, int c);
+int auto_fixed_window(kzg_ctx* ctx, uint64_t n_points);   // widest window whose table fits the memory budget
 
 // ---- setup_g2.cu (K3') ---------------------------------------------------------------------
 // [s^(first+i)]G2, i < n, as 96-byte compressed points (device)
@@ -176,6 +196,8 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
                    G1Xyzz* result_dev);
 // sum_b (b+1) * A_b, A_b = sum_k parts[b*T + k] with T = 2^logT partials per bucket (msm_tail.cu)
 int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, G1Xyzz* result_dev);
+// out_dev[0..count) = infinity
+int32_t set_infinity(kzg_ctx* ctx, G1Xyzz* out_dev, uint32_t count);
 // sum `count` XYZZ points (device) into out_dev[0]
 int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* out_dev);
 // XYZZ (device) x count -> 48-byte compressed (device)
@@ -185,6 +207,7 @@ int32_t finalize_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, uint
 struct PeerMailbox {
   G1Xyzz slot[KZG_P2P_DEPTH][KZG_MAX_PEERS];     // [call number mod depth][source rank]
   uint32_t flag[KZG_P2P_DEPTH][KZG_MAX_PEERS];   // sequence number of the partial in the slot
+  uint32_t dead[KZG_MAX_PEERS];                  // != 0: that rank gave up (timed out) in the call of this number — sticky
 };
 struct PeerTable { PeerMailbox* box[KZG_MAX_PEERS]; };
 // `ctx` supplies the stream, `owner` the mailboxes; seq = number of this collective call (same on every rank)
@@ -214,6 +237,65 @@ int32_t batch_invert_inplace(kzg_ctx* ctx, Fq* v, uint64_t N, Fq* ws, uint64_t t
 int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const char* tab_pitched,
                         uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
                         const uint32_t** seg_out, const uint32_t** iota_out, uint64_t* entries_out);
+
+// ---- engine_one.cu: the single-device engine API (one_* = the kzg_* entry point of the same name on ONE device) ----
+int32_t one_ctx_create(kzg_ctx** out, int32_t device_id);
+void one_ctx_destroy(kzg_ctx* ctx);
+const char* one_last_error(const kzg_ctx* ctx);
+int32_t one_ctx_sync(kzg_ctx* ctx);
+int32_t one_ctx_timer_start(kzg_ctx* ctx);
+int32_t one_ctx_timer_stop(kzg_ctx* ctx, float* ms);
+uint64_t one_ctx_launch_count(const kzg_ctx* ctx);
+void* one_ctx_stream(const kzg_ctx* ctx);
+float one_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which);
+int32_t one_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value);
+int32_t one_setup_generate(kzg_ctx* ctx, const uint8_t secret_be[32], uint64_t first, uint64_t n, kzg_setup** out);
+int32_t one_setup_import_g1(kzg_ctx* ctx, const uint8_t* g1_c48, uint64_t n, kzg_setup** out);
+int32_t one_setup_export_g1(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count, uint8_t* out_c48);
+uint64_t one_setup_len(const kzg_setup* s);
+int32_t one_setup_generate_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t secret_be[32], uint64_t count);
+int32_t one_setup_import_g2(kzg_ctx* ctx, kzg_setup* s, const uint8_t* g2_c96, uint64_t count);
+int32_t one_setup_export_g2(kzg_ctx* ctx, const kzg_setup* s, uint64_t first, uint64_t count, uint8_t* out_c96);
+uint64_t one_setup_g2_len(const kzg_setup* s);
+int32_t one_msm_plan(const kzg_ctx* ctx, const kzg_setup* s, uint64_t n, int32_t plan[5]);
+void one_setup_destroy(kzg_setup* s);
+int32_t one_setup_prepare_msm(kzg_ctx* ctx, kzg_setup* s, int32_t window_bits);
+int32_t one_setup_prepare_fixed(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int32_t window_bits);
+int32_t one_msm_g1_partial_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, void* partial_dev);
+int32_t one_msm_g1_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]);
+int32_t one_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, uint8_t out_c48[48]);
+int32_t one_msm_g1_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket);
+int32_t one_msm_g1_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket);
+int32_t one_msm_g1_sharded_submit_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, int32_t* ticket);
+int32_t one_msm_g1_sharded_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32, uint64_t n, int32_t* ticket);
+int32_t one_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]);
+int32_t one_p2p_init(kzg_ctx* ctx, int32_t world, int32_t rank, uint8_t handle_out[64]);
+int32_t one_p2p_connect(kzg_ctx* ctx, const uint8_t* handles);
+int32_t one_msm_g1_sharded_dev(kzg_ctx* ctx, const kzg_setup* s, const void* scalars_dev, uint64_t n, uint8_t out_c48[48]);
+int32_t one_g1_combine_dev(kzg_ctx* ctx, const void* partials_dev, uint64_t count, uint8_t out_c48[48]);
+int32_t one_commit(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n, uint8_t out_c48[48]);
+int32_t one_evaluate_dev(kzg_ctx* ctx, const void* coeffs_dev, uint64_t n, const uint8_t z_le[32], uint8_t y_le[32]);
+int32_t one_evaluate(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], uint8_t y_le[32]);
+int32_t one_quotient(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], const uint8_t* y_le, uint8_t* q_le32, uint64_t* q_len);
+int32_t one_open(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], const uint8_t* y_expected_le, uint8_t y_out_le[32], uint8_t proof_c48[48]);
+int32_t one_commit_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n, void* out_c48_dev);
+int32_t one_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n, const void* z_dev, void* y_dev, void* proofs_c48_dev);
+int32_t one_commit_open_batch_dev(kzg_ctx* ctx, const kzg_setup* s, const void* coeffs_dev, uint64_t blobs, uint64_t n, const void* z_dev, void* commits_c48_dev, void* y_dev, void* proofs_c48_dev);
+int32_t one_commit_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n, uint8_t* out_c48);
+int32_t one_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n, const uint8_t* z_le32, uint8_t* y_le32, uint8_t* proofs_c48);
+int32_t one_commit_open_batch(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* coeffs_le32, uint64_t blobs, uint64_t n, const uint8_t* z_le32, uint8_t* commits_c48, uint8_t* y_le32, uint8_t* proofs_c48);
+int32_t one_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s);
+int32_t one_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s);
+int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host, bool sharded, int32_t* ticket);
+void copy_options(kzg_ctx* dst, const kzg_ctx* src);
+// stages the coefficients, runs the scan, applies divide_by_root's error rules; *q_dev = trimmed quotient on the device
+int32_t quotient_core(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], const uint8_t* y_le,
+                      uint8_t y_out[32], uint8_t** q_dev, uint64_t* q_len);
+// mailbox of a context for the peer exchange, and the wiring when all ranks live in one process (plain peer pointers)
+int32_t p2p_alloc_box(kzg_ctx* ctx, int32_t world, int32_t rank);
+int32_t p2p_attach_local(kzg_ctx* ctx, void* const* boxes);
+// blobs x n coefficients on the device: is any coefficient at index >= limit non-zero mod r?  (poly.cu; synchronises)
+int32_t any_nonzero_beyond(kzg_ctx* ctx, const uint8_t* coeffs_dev, uint64_t blobs, uint64_t n, uint64_t limit, bool* any);
 
 // ---- probe.cu --------------------------------------------------------------------------------
 int32_t probe_imad(kzg_ctx* ctx, double* wide_mac_per_s);

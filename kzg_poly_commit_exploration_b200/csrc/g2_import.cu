@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(64)
 k_g2_validate(const uint8_t* __restrict__ in_c96, uint64_t n, unsigned long long* __restrict__ bad) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint8_t buf[96];
+  __align__(16) uint8_t buf[96];      // filled with 128-bit stores
   const uint4* q = reinterpret_cast<const uint4*>(in_c96 + i * 96);
 #pragma unroll
   for (int k = 0; k < 6; k++) reinterpret_cast<uint4*>(buf)[k] = __ldg(q + k);

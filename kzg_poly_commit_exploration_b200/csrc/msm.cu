@@ -165,6 +165,12 @@ __global__ void k_set_inf(G1Xyzz* out, uint32_t count) {
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
+int32_t set_infinity(kzg_ctx* ctx, G1Xyzz* out_dev, uint32_t count) {
+  k_set_inf<<<blocks_for(count ? count : 1, 128), 128, 0, ctx->stream>>>(out_dev, count);
+  KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
 // affine halving rounds by problem size (measured, profiles/sweep_tree_rounds_r01.txt, sweep_lanes_r01.txt): one per
 // doubling of the entry count from 2^20 entries on - 2 at n = 2^17, 5 at n = 2^20 (c = 16), at most 6.  A round's
 // inversion chain is ~0.15 ms of latency; with several calls in flight (lanes) that latency is covered by the bulk
@@ -178,11 +184,7 @@ int auto_tree_rounds(uint64_t entries) {
 
 int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
                    G1Xyzz* result_dev) {
-  if (n == 0) {
-    k_set_inf<<<1, 32, 0, ctx->stream>>>(result_dev, 1);
-    KZG_LAUNCHED(ctx);
-    return KZG_OK;
-  }
+  if (n == 0) return set_infinity(ctx, result_dev, 1);
   if (!s->msm_tab) return fail(ctx, KZG_E_BAD_ARG, "msm table not prepared");
   const int c = s->msm_c, W = s->msm_w;
   const uint32_t half = 1u << (c - 1);

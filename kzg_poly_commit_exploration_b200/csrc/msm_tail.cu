@@ -388,7 +388,10 @@ k_sum_coop(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ o
 // affine and compresses.  Mailbox slots are KZG_P2P_DEPTH = 2 L deep (L = KZG_MAX_LANES), indexed by the call number: a
 // rank has at most L calls in flight (submit k + L only after waiting for k), k completes on a rank only when EVERY rank
 // has published k, and a rank publishes k only after it finished k - L; so when call k + L overwrites the slot of call
-// k - L every rank is done reading it.  A bounded spin turns a dead peer into an error instead of a hang.
+// k - L every rank is done reading it.  A bounded spin (20 s by default, option p2p_timeout_ms, counted with the device's
+// own clock rate) turns a dead peer into an error instead of a hang, and that error is COLLECTIVE: the rank that gives
+// up writes a sticky word into every peer's mailbox, peers check it while they wait and once more before they return,
+// and the contexts refuse further collective calls (their sequence numbers are no longer in step).
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -405,8 +408,9 @@ k_exchange_combine(const G1Xyzz* __restrict__ mine, PeerTable peers, int world, 
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t par = seq & (KZG_P2P_DEPTH - 1);
   PeerMailbox* my = peers.box[rank];
-  int ok = 1;
-  if (w == 0 && lane < (uint32_t)world) {
+  const bool talker = w == 0 && lane < (uint32_t)world;
+  int timed_out = 0, peer_dead = 0;
+  if (talker) {
     const uint4* src = reinterpret_cast<const uint4*>(mine);
     PeerMailbox* mb = peers.box[lane];
     volatile uint4* dst = reinterpret_cast<volatile uint4*>(&mb->slot[par][rank]);
@@ -416,12 +420,21 @@ k_exchange_combine(const G1Xyzz* __restrict__ mine, PeerTable peers, int world, 
     st_release_sys(&mb->flag[par][rank], seq);
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(&my->flag[par][lane]) - seq) < 0) {
-      if (clock64() - t0 > timeout_cycles) { ok = 0; break; }
+      if (ld_acquire_sys(&my->dead[lane]) != 0) { peer_dead = 1; break; }      // that rank has given up: do not wait for it
+      if (clock64() - t0 > timeout_cycles) { timed_out = 1; break; }
       __nanosleep(64);
     }
+    // everything has landed — but a peer may have stopped waiting for US before we published: then it returned an
+    // error for this call, and so must we (all ranks agree on the outcome of a collective call)
+    if (!timed_out && !peer_dead && ld_acquire_sys(&my->dead[lane]) != 0) peer_dead = 1;
   }
-  if (!__syncthreads_and(ok)) {
-    if (threadIdx.x == 0) *status = 1u;
+  const int any_timeout = __syncthreads_or(timed_out);
+  const int any_dead = __syncthreads_or(peer_dead);
+  if (any_timeout || any_dead) {
+    // give the call up on EVERY rank: the sticky word tells peers that are still waiting (or arrive later) to fail too.
+    // What remains is the window of one NVLink round trip between a rank's last look at `dead` and a peer's store to it.
+    if (talker) st_release_sys(&peers.box[lane]->dead[rank], seq ? seq : 1u);
+    if (threadIdx.x == 0) *status = any_timeout ? 1u : 2u;
     return;
   }
   G1Xyzz X;

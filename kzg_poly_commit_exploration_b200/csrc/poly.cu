@@ -121,16 +121,41 @@ __global__ void k_zero32(uint8_t* y, uint32_t blobs) {
   if (i < blobs * 8) reinterpret_cast<uint32_t*>(y)[i] = 0;
 }
 
-int32_t poly_eval_quotient(kzg_ctx* ctx, const uint8_t* coeffs_dev, uint64_t blobs, uint64_t n,
-                           const uint8_t* z_dev, uint8_t* y_dev, uint8_t* q_dev) {
-  if (blobs == 0) return KZG_OK;
-  if (n == 0) {  // empty polynomial evaluates to 0 (src/polynomial.rs:113)
-    k_zero32<<<(unsigned)((blobs * 8 + 255) / 256), 256, 0, ctx->stream>>>(y_dev, (uint32_t)blobs);
-    KZG_LAUNCHED(ctx);
-    return KZG_OK;
-  }
+// Polynomial::try_from trims trailing zeros (src/polynomial.rs:63-72) and commit compares the TRIMMED length with the
+// setup (:201-205): rows of a device-resident batch that are longer than the setup are fine when everything from
+// index `limit` on is zero mod r.  One pass over the tail columns, result through a flag word.
+__global__ void k_any_nonzero_beyond(const uint8_t* __restrict__ coeffs, uint64_t blobs, uint64_t n, uint64_t limit,
+                                     uint32_t* __restrict__ flag) {
+  const uint64_t tail = n - limit;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= blobs * tail) return;
+  const uint64_t row = i / tail, col = limit + i % tail;
+  Fr c; ld_fr(c, coeffs + (row * n + col) * 32);
+  fr_canon_reduce(c);
+  if (!is_zero(c)) *flag = 1u;
+}
+
+int32_t any_nonzero_beyond(kzg_ctx* ctx, const uint8_t* coeffs_dev, uint64_t blobs, uint64_t n, uint64_t limit, bool* any) {
+  *any = false;
+  if (blobs == 0 || limit >= n) return KZG_OK;
+  void* m;
+  KZG_TRY(scratch_get(ctx, SCR_MISC, 1024, &m));
+  uint32_t* flag = reinterpret_cast<uint32_t*>(m) + 200;       // clear of the 192-byte result slot other calls keep here
+  KZG_CUDA_OK(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+  const uint64_t total = blobs * (n - limit);
+  k_any_nonzero_beyond<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(coeffs_dev, blobs, n, limit, flag);
+  KZG_LAUNCHED(ctx);
+  uint32_t h = 0;
+  KZG_CUDA_OK(ctx, cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *any = h != 0;
+  return KZG_OK;
+}
+
+// one launch set covers at most 65535 polynomials (grid.y); larger batches run in row chunks
+static int32_t poly_eval_quotient_rows(kzg_ctx* ctx, const uint8_t* coeffs_dev, uint64_t blobs, uint64_t n,
+                                       const uint8_t* z_dev, uint8_t* y_dev, uint8_t* q_dev) {
   uint32_t nseg = (uint32_t)((n + POLY_SEG - 1) / POLY_SEG);
-  if (blobs > 65535) return fail(ctx, KZG_E_BAD_ARG, "poly_eval_quotient: more than 65535 polynomials per call");
   dim3 grid(nseg, (unsigned)blobs);
   Fr* tin = nullptr;
   if (nseg > 1) {
@@ -145,6 +170,23 @@ int32_t poly_eval_quotient(kzg_ctx* ctx, const uint8_t* coeffs_dev, uint64_t blo
   }
   k_poly_scan<1><<<grid, POLY_THREADS, 0, ctx->stream>>>(coeffs_dev, n, z_dev, tin, nullptr, y_dev, q_dev, nseg);
   KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
+int32_t poly_eval_quotient(kzg_ctx* ctx, const uint8_t* coeffs_dev, uint64_t blobs, uint64_t n,
+                           const uint8_t* z_dev, uint8_t* y_dev, uint8_t* q_dev) {
+  if (blobs == 0) return KZG_OK;
+  if (n == 0) {  // empty polynomial evaluates to 0 (src/polynomial.rs:113)
+    k_zero32<<<(unsigned)((blobs * 8 + 255) / 256), 256, 0, ctx->stream>>>(y_dev, (uint32_t)blobs);
+    KZG_LAUNCHED(ctx);
+    return KZG_OK;
+  }
+  constexpr uint64_t MAX_ROWS = 65535;            // grid.y
+  for (uint64_t r0 = 0; r0 < blobs; r0 += MAX_ROWS) {
+    const uint64_t rows = blobs - r0 < MAX_ROWS ? blobs - r0 : MAX_ROWS;
+    KZG_TRY(poly_eval_quotient_rows(ctx, coeffs_dev + r0 * n * 32, rows, n, z_dev + r0 * 32, y_dev + r0 * 32,
+                                    q_dev ? q_dev + r0 * n * 32 : nullptr));
+  }
   return KZG_OK;
 }
 

@@ -369,10 +369,33 @@ int32_t build_msm_table(kzg_ctx* ctx, kzg_setup* s, int c) {
   return KZG_OK;
 }
 
+// bytes of the fixed-base table for n_points bases at window c (W windows x 2^(c-1) multiples per base and window)
+uint64_t fixed_table_bytes(uint64_t n_points, int c) {
+  return (uint64_t)windows_for(c) * n_points * ((uint64_t)1 << (c - 1)) * sizeof(G1Affine);
+}
+
+// Window of the fixed-base table when the caller does not name one: blob throughput is ~ 1 / W(c) and random
+// 96-byte reads cost the same over 100 GiB as over 1 GiB, so the widest window whose table (plus the
+// transient folded copy) fits the memory budget wins.  Budget = option "fixed_table_max_bytes", else 60 % of the
+// memory that is free right now (cudaMemGetInfo): the rest stays for the batch scratch (~8 GiB at 2048 rows of 4096)
+// and for other tenants of the device.  n = 4096 on an empty B200: c = 15 (102 GiB); with 64 GiB free: c = 14 (51 GiB).
+int auto_fixed_window(kzg_ctx* ctx, uint64_t n_points) {
+  size_t free_b = 0, total_b = 0;
+  uint64_t budget = ctx->opt_fixed_table_max_bytes > 0 ? (uint64_t)ctx->opt_fixed_table_max_bytes : 0;
+  if (!budget) {
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 10; }
+    budget = (uint64_t)((double)free_b * 0.60);
+  }
+  int best = 2;
+  for (int c = 2; c <= 15; c++)
+    if (fixed_table_bytes(n_points ? n_points : 1, c) <= budget) best = c;
+  return best;
+}
+
 int32_t build_fixed_table(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int c) {
-  if (c <= 0) c = ctx->opt_fixed_window > 0 ? ctx->opt_fixed_window : 10;
-  if (c < 2 || c > 16) return fail(ctx, KZG_E_BAD_ARG, "fixed window_bits out of range [2,16]");
   if (n_points > s->n) n_points = s->n;
+  if (c <= 0) c = ctx->opt_fixed_window > 0 ? ctx->opt_fixed_window : auto_fixed_window(ctx, n_points);
+  if (c < 2 || c > 16) return fail(ctx, KZG_E_BAD_ARG, "fixed window_bits out of range [2,16]");
   if (s->fix_tab && s->fix_c == c && s->fix_n >= n_points) return KZG_OK;
   if (s->fix_tab) { cudaFree(s->fix_tab); s->fix_tab = nullptr; s->fix_n = 0; }
   if (n_points == 0) return KZG_OK;

@@ -18,12 +18,29 @@ def _ptr(x):
 
 
 class Context:
-    def __init__(self, device: int = 0):
+    """One CUDA device (`Context(0)`) or several devices driven from this process (`Context([0, 1, 2, 3])`,
+    kzg_ctx_create_multi): the same calls then shard internally (see include/kzg_b200.h)."""
+
+    def __init__(self, device=0):
         self._h = C.c_void_p()
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int32 * len(device))(*device)
+            st = N.lib().kzg_ctx_create_multi(C.byref(self._h), ids, len(device))
+            if st != N.KZG_OK:
+                raise N.KzgNativeError(st, f"kzg_ctx_create_multi(devices={list(device)}) failed: no usable CUDA devices or no peer "
+                                           "access between them (no CPU fallback)")
+            self.device = int(device[0])
+            self.devices = [int(d) for d in device]
+            return
         st = N.lib().kzg_ctx_create(C.byref(self._h), device)
         if st != N.KZG_OK:
             raise N.KzgNativeError(st, f"kzg_ctx_create(device={device}) failed: no usable CUDA device (no CPU fallback)")
         self.device = device
+        self.devices = [device]
+
+    @property
+    def device_count(self) -> int:
+        return int(N.lib().kzg_ctx_device_count(self._h))
 
     def close(self):
         if self._h:
@@ -268,7 +285,13 @@ class Setup:
         self.ctx.check(N.lib().kzg_setup_prepare_msm(self.ctx._h, self._h, window_bits))
 
     def prepare_fixed(self, n_points: int, window_bits: int = 0):
+        """window_bits = 0: the widest window whose table fits the memory budget (kzg_setup_fixed_plan tells which)"""
         self.ctx.check(N.lib().kzg_setup_prepare_fixed(self.ctx._h, self._h, n_points, window_bits))
+
+    def fixed_plan(self) -> dict:
+        p = (C.c_int64 * 4)()
+        self.ctx.check(N.lib().kzg_setup_fixed_plan(self._h, p))
+        return {"c": int(p[0]), "W": int(p[1]), "points": int(p[2]), "table_bytes": int(p[3])}
 
     def close(self):
         if self._h:
