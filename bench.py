@@ -635,7 +635,7 @@ def blob_batch(args, R, pkg, synthetic, ctx, devices, pk):
         ctx.set_option("setup_layout", 2)
     setup = ctx.setup_generate(synthetic.BENCH_SECRET_BE, n)
     t0 = time.perf_counter()
-    setup.prepare_fixed(n, args.fixed_window)      # 0 = the widest window whose table fits 60 % of the free memory
+    setup.prepare_fixed(n, args.fixed_window)      # 0 = the widest window whose table fits 66 % of the free memory
     ctx.sync()
     table_s = time.perf_counter() - t0
     fplan = setup.fixed_plan()
@@ -755,7 +755,7 @@ def blob_batch(args, R, pkg, synthetic, ctx, devices, pk):
                    "d2h_bytes_per_batch": blobs_total * 128},
            "config": {"workload": f"{blobs_total} blobs x {n} coefficients (BASELINE config C4), commit + proof, sharded by blob",
                       "fixed_base_window_bits": fplan["c"], "lookups_per_coefficient": fplan["W"],
-                      "window_choice": "given" if args.fixed_window else "auto: widest table within 60 % of the free device memory",
+                      "window_choice": "given" if args.fixed_window else "auto: widest table within 66 % of the free device memory",
                       "table_gib": round(fplan["table_bytes"] / 2**30, 2), "table_build_s": round(table_s, 2)},
            "dev_equals_e2e": bool(same), "checksums_match_golden": gold_ok,
            "roofline": {"bound": "int32-multiply", "unit": "T wide-MAC/s",

@@ -127,7 +127,7 @@ void kzg_setup_destroy(kzg_setup* s);
 int32_t kzg_setup_prepare_msm(kzg_ctx* ctx, kzg_setup* s, int32_t window_bits);
 int32_t kzg_setup_prepare_fixed(kzg_ctx* ctx, kzg_setup* s, uint64_t n_points, int32_t window_bits);
 /* window_bits = 0 picks the widest window (<= 15) whose table fits the memory budget: option "fixed_table_max_bytes",
- * else 60 % of the device memory free at the time (blob throughput is ~ 1 / ceil(255 / c); n = 4096: c = 15 is 102 GiB,
+ * else 66 % of the device memory free at the time (blob throughput is ~ 1 / ceil(255 / c); n = 4096: c = 15 is 102 GiB,
  * c = 14 51 GiB, c = 13 26 GiB).  plan = { window_bits c, lookups per coefficient W, points covered, table bytes }. */
 int32_t kzg_setup_fixed_plan(const kzg_setup* s, int64_t plan[4]);
 

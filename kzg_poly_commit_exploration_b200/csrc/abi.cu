@@ -182,6 +182,7 @@ int32_t group_create(kzg_ctx** out, const int32_t* ids, int32_t n) {
   for (int g = 1; g < n; g++) S->workers.emplace_back(new Worker(ids[g]));
   head->group_state = S;
   head->members = m;
+  for (int a = 0; a < n; a++) for (int b = a + 1; b < n; b++) if (ids[a] == ids[b]) head->group_shares_devices = true;
   for (kzg_ctx* c : m) c->group_head = head;
   *out = head;
   return KZG_OK;
@@ -211,6 +212,11 @@ int32_t group_msm_submit(kzg_ctx* head, const kzg_setup* S, const void* scalars,
     KZG_TRY(submit_common(head, S->shards[0], scalars, n, host, false, &T.member_ticket[0]));
   } else {
     const uint8_t* base = reinterpret_cast<const uint8_t*>(scalars);
+    // members that share a device: allocate everywhere first, launch afterwards (see reserve_call, engine_one.cu)
+    if (head->group_shares_devices)
+      KZG_TRY(for_members(head, [&](int g, kzg_ctx* m) {
+        return reserve_call(m, S->shards[(size_t)g], base + S->shard_off[(size_t)g] * 32, shard_share(S, g, n), host);
+      }));
     int32_t st = for_members(head, [&](int g, kzg_ctx* m) {
       return submit_common(m, S->shards[(size_t)g], base + S->shard_off[(size_t)g] * 32, shard_share(S, g, n), host, true,
                            &T.member_ticket[g]);

@@ -46,7 +46,7 @@ struct kzg_ctx {
   void* g2table = nullptr;             // [20][4096] signed-window multiples of the G2 generator (setup_g2.cu)
   int opt_msm_window = 0;              // 0 = auto
   int opt_fixed_window = 0;            // 0 = auto: the widest window whose table fits the memory budget (setup.cu auto_fixed_window)
-  int64_t opt_fixed_table_max_bytes = 0;   // budget of that choice; 0 = 60 % of the device memory free at the time
+  int64_t opt_fixed_table_max_bytes = 0;   // budget of that choice; 0 = 66 % of the device memory free at the time
   int opt_reduce_chunk = 16;
   int opt_heavy_cap = 1024;
   int opt_acc_split = -1;              // log2(threads per bucket), -1 = auto
@@ -92,6 +92,7 @@ struct kzg_ctx {
   void* p2p_box[kzg::KZG_MAX_PEERS] = {};
   int sm_clock_khz = 1965000;          // cudaDevAttrClockRate: clock64() ticks per ms, for the exchange timeout
   long long p2p_timeout_cycles = 20000ll * 1965000;   // spinning time before a missing peer becomes an error (20 s; option p2p_timeout_ms)
+  uint64_t reserved_n = 0;             // largest sum this lane's arenas have been sized for ahead of time (reserve_call)
   int last_lane = 0;                   // lane the most recent bulk call ran on (its events feed kzg_ctx_last_kernel_ms)
   // single-process multi-GPU (kzg_ctx_create_multi, abi.cu): this context is the head of a GROUP of per-device member
   // contexts; members[0] == this.  Every member has a host worker thread that issues its launches, so that one caller
@@ -99,6 +100,7 @@ struct kzg_ctx {
   std::vector<kzg_ctx*> members;
   kzg_ctx* group_head = nullptr;       // set on every member (also on the head itself) of a group
   void* group_state = nullptr;         // abi.cu: worker threads, group tickets (owned by the head)
+  bool group_shares_devices = false;   // head: two members sit on one device (testing on a single-GPU box): submits run in two phases
   int opt_setup_layout = 0;            // group setups: 0 = auto (replicate up to 2^16 points, else shard by point range), 1 = range, 2 = replicated
 };
 
@@ -288,6 +290,7 @@ int32_t one_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s);
 int32_t one_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s);
 int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host, bool sharded, int32_t* ticket);
 void copy_options(kzg_ctx* dst, const kzg_ctx* src);
+int32_t reserve_call(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host);
 // stages the coefficients, runs the scan, applies divide_by_root's error rules; *q_dev = trimmed quotient on the device
 int32_t quotient_core(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], const uint8_t* y_le,
                       uint8_t y_out[32], uint8_t** q_dev, uint64_t* q_len);

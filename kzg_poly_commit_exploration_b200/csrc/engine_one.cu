@@ -6,6 +6,7 @@
 //   SetupArtifactsGenerator                                                    src/trusted_setup.rs:20-78
 // There is no CPU fallback for any bulk operation.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "engine.cuh"
 
@@ -104,9 +105,22 @@ void update_timers(kzg_ctx* ctx) {
 
 namespace kzg {
 
+// A context owns up to 2 x lanes streams, and the kernels of the peer exchange SPIN until other streams (of other devices,
+// or of another member on the same device) have made progress.  With more streams than hardware queues
+// (CUDA_DEVICE_MAX_CONNECTIONS, default 8) the driver multiplexes streams onto queues, and a spinning kernel then blocks
+// unrelated streams that happen to share its queue — across devices that can close a cycle.  Ask for 32 queues unless
+// the host decided otherwise; it only takes effect if CUDA is not initialised yet in this process.
+static void want_hardware_queues() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
+
 int32_t one_ctx_create(kzg_ctx** out, int32_t device_id) {
   if (!out) return KZG_E_BAD_ARG;
   *out = nullptr;
+  want_hardware_queues();
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device_id < 0 || device_id >= count) {
     cudaGetLastError();
@@ -453,6 +467,59 @@ static int32_t lane_of(kzg_ctx* ctx, uint32_t ticket, kzg_ctx** lane) {
   return KZG_OK;
 }
 
+// lane + result slot + staging buffer of the next ticket, allocated on first use
+static int32_t pending_slot(kzg_ctx* ctx, uint64_t n, bool host, kzg_ctx** lane_out, int* lane_index_out, kzg_ctx::Pending** q_out) {
+  const uint32_t t = ctx->next_ticket;
+  kzg_ctx* lane;
+  KZG_TRY(lane_of(ctx, t, &lane));
+  const int lane_index = (int)(t % (uint32_t)ctx->lanes_in_use);
+  kzg_ctx::Pending& q = ctx->pending[lane_index];
+  if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "every lane has a call in flight: wait for the oldest ticket first");
+  if (!q.copied) {
+    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.copied, cudaEventDisableTiming));
+    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+    KZG_CUDA_OK(ctx, cudaMalloc(&q.result, 512));
+    KZG_CUDA_OK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&q.out_host), 64, cudaHostAllocDefault));
+  }
+  if (host) {
+    const size_t bytes = n ? n * 32 : 32;
+    if (q.cap < bytes) {
+      if (q.scalars) { KZG_CUDA_OK(ctx, cudaFree(q.scalars)); q.scalars = nullptr; q.cap = 0; }
+      KZG_CUDA_OK(ctx, cudaMalloc(&q.scalars, bytes));
+      q.cap = bytes;
+    }
+  }
+  *lane_out = lane; *lane_index_out = lane_index; *q_out = &q;
+  return KZG_OK;
+}
+
+// Everything the NEXT submitted call of n scalars will allocate, allocated now: the lane (streams, events), its result
+// slot and staging buffer, the setup's table, and the lane's scratch arenas (sized by a dry run of the sum, whose result
+// is dropped).  Device allocations synchronise with the device; a group whose members SHARE a device must therefore not
+// allocate between one member's exchange kernel (which spins until its peers publish) and another member's launches —
+// abi.cu reserves on every member first, then submits (two phases).  A no-op once the lane has seen this size.
+int32_t reserve_call(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host) {
+  if (!ctx || !s) return KZG_E_BAD_ARG;
+  if (n > s->n) return fail(ctx, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
+  DeviceGuard g(ctx->device);
+  kzg_ctx* lane; int lane_index; kzg_ctx::Pending* q;
+  KZG_TRY(pending_slot(ctx, n, host, &lane, &lane_index, &q));
+  if (n == 0 || lane->reserved_n >= n) return KZG_OK;
+  if (!s->msm_tab && !(s->fix_tab && n <= s->fix_n)) KZG_TRY(ensure_msm_table(ctx, s));
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint8_t* sc = reinterpret_cast<const uint8_t*>(scalars);
+  if (host) {      // whatever the staging buffer holds are valid scalars (any 32 bytes are): the run only sizes the arenas
+    KZG_CUDA_OK(ctx, cudaMemsetAsync(q->scalars, 0x5a, n * 32, lane->stream));
+    sc = reinterpret_cast<const uint8_t*>(q->scalars);
+  }
+  int32_t st = msm_any(lane, s, sc, n, reinterpret_cast<G1Xyzz*>(q->result));
+  if (st == KZG_OK) st = finalize_points(lane, reinterpret_cast<G1Xyzz*>(q->result), 1, reinterpret_cast<uint8_t*>(q->result) + 256);
+  if (st != KZG_OK) { if (lane != ctx) ctx->err = lane->err; return st; }
+  KZG_CUDA_OK(ctx, cudaStreamSynchronize(lane->stream));
+  lane->reserved_n = n;
+  return KZG_OK;
+}
+
 // host == true: `scalars` is a host buffer, copied on the lane's copy stream (device pointers may live on ANY device
 // the context's device has peer access to: the kernels read them over NVLink); sharded == true: the result is the
 // fold of every rank's partial (peer exchange), else this context's own sum
@@ -466,29 +533,15 @@ int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uin
                                  "no longer in step, create the contexts again");
   DeviceGuard g(ctx->device);
   const uint32_t t = ctx->next_ticket;
-  kzg_ctx* lane;
-  KZG_TRY(lane_of(ctx, t, &lane));
-  const int lane_index = (int)(t % (uint32_t)ctx->lanes_in_use);
-  kzg_ctx::Pending& q = ctx->pending[lane_index];
-  if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "every lane has a call in flight: wait for the oldest ticket first");
+  kzg_ctx* lane; int lane_index; kzg_ctx::Pending* qp;
+  KZG_TRY(pending_slot(ctx, n, host, &lane, &lane_index, &qp));
+  kzg_ctx::Pending& q = *qp;
   if (n && !s->msm_tab && !(s->fix_tab && n <= s->fix_n)) {      // built once, on the main lane, before any lane reads it
     KZG_TRY(ensure_msm_table(ctx, s));
     KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  if (!q.copied) {
-    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.copied, cudaEventDisableTiming));
-    KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
-    KZG_CUDA_OK(ctx, cudaMalloc(&q.result, 512));
-    KZG_CUDA_OK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&q.out_host), 64, cudaHostAllocDefault));
-  }
   const uint8_t* dev_scalars = reinterpret_cast<const uint8_t*>(scalars);
   if (host) {
-    const size_t bytes = n ? n * 32 : 32;
-    if (q.cap < bytes) {
-      if (q.scalars) { KZG_CUDA_OK(ctx, cudaFree(q.scalars)); q.scalars = nullptr; q.cap = 0; }
-      KZG_CUDA_OK(ctx, cudaMalloc(&q.scalars, bytes));
-      q.cap = bytes;
-    }
     if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.scalars, scalars, n * 32, cudaMemcpyHostToDevice, lane->copy_stream));
     KZG_CUDA_OK(ctx, cudaEventRecord(q.copied, lane->copy_stream));
     KZG_CUDA_OK(ctx, cudaStreamWaitEvent(lane->stream, q.copied, 0));

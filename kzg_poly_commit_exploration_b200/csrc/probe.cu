@@ -10,36 +10,36 @@ namespace kzg {
 constexpr int PROBE_ITERS = 2048;
 constexpr int PROBE_CHAINS = 8;
 
-// The multiplier pipe on its own: 8 independent chains per thread of p = a * b (32 x 32 -> 64, IMAD.WIDE.U32 with a zero
-// addend), each product folded back into its multiplicand with ONE LOP3 so that every product is distinct and live.
-// Round 1's probe accumulated (`mad.wide.u32 acc, a, b, acc` four times on the same operands): ptxas folded three of
-// the four products away and split the accumulation into IADD3 / IADD3.X pairs, so it timed one IMAD.WIDE plus eight
-// adds per "four multiply-adds" and under-reported the pipe.  SASS of this loop body (cuobjdump, profiles/): 32
-// IMAD.WIDE.U32 + 32 LOP3.LUT + loop overhead, nothing else.  ptxas will not emit IMAD.WIDE with a 64-bit addend for an
-// accumulation chain (it prefers the product with RZ plus IADD3 pairs), which is why the figure is the multiplier's issue
-// rate and the additions of a real multiply-ACCUMULATE come on top (on the ALU pipe, or fused as the carry-chained
+// The multiplier pipe on its own: 8 independent chains per thread of p <- lo(p) * hi(p) (32 x 32 -> 64): every step is
+// exactly ONE IMAD.WIDE.U32 (zero addend) whose two result halves are the next step's operands, so there is nothing for
+// ptxas to fold and no companion instruction on another pipe.  History: round 1's probe accumulated the same product four
+// times (`mad.wide.u32 acc, a, b, acc`), ptxas folded three of the four away and split the accumulation into IADD3 pairs,
+// so it timed one IMAD.WIDE plus eight adds per "four multiply-adds"; a first repair consumed each product with a LOP3,
+// and measured IMAD.WIDE + LOP3 back to back (ALU instructions do not hide under wide multiplies on this chip,
+// profiles/ubench_imad_r01.txt): 30.6 lanes/clk/SM, BELOW the shipped field product.  SASS of this loop body
+// (cuobjdump, profiles/probe_imad_r02_sass.txt): 32 x IMAD.WIDE.U32 Rp, Rlo, Rhi, RZ + loop overhead.
+// The additions of a real multiply-ACCUMULATE come on top (IADD3 pairs on the ALU pipe, or fused as the carry-chained
 // IMAD.WIDE.U32.X the field code uses, which holds the pipe longer: kzg_probe_fq_mul measures that one).
 __global__ void __launch_bounds__(256) k_probe_imad(uint32_t* out, uint32_t seed) {
-  uint32_t a[PROBE_CHAINS];
-  const uint32_t b = ((seed ^ 0x9E3779B9u) + blockIdx.x * 977u + threadIdx.x) | 0x80000001u;
+  uint64_t p[PROBE_CHAINS];
 #pragma unroll
-  for (int k = 0; k < PROBE_CHAINS; k++) a[k] = seed + threadIdx.x * 2654435761u + (uint32_t)k * 0x85EBCA6Bu;
+  for (int k = 0; k < PROBE_CHAINS; k++)
+    p[k] = ((uint64_t)(seed + threadIdx.x * 2654435761u + (uint32_t)k * 0x85EBCA6Bu) << 32) | ((seed ^ 0x9E3779B9u) + blockIdx.x * 977u + (uint32_t)k);
 #pragma unroll 1
   for (int it = 0; it < PROBE_ITERS; it++) {
 #pragma unroll
     for (int rep = 0; rep < 4; rep++) {
 #pragma unroll
       for (int k = 0; k < PROBE_CHAINS; k++) {
-        uint64_t p;
-        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a[k]), "r"(b));
-        a[k] = (uint32_t)(p >> 32) ^ (uint32_t)p;
+        const uint32_t lo = (uint32_t)p[k], hi = (uint32_t)(p[k] >> 32);
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p[k]) : "r"(lo), "r"(hi));
       }
     }
   }
-  uint32_t s = 0;
+  uint64_t s = 0;
 #pragma unroll
-  for (int k = 0; k < PROBE_CHAINS; k++) s ^= a[k];
-  if (s == 0x1234567u) out[0] = s;   // never true in practice; keeps the chains live
+  for (int k = 0; k < PROBE_CHAINS; k++) s ^= p[k];
+  if (s == 0x1234567ull) out[0] = (uint32_t)s;   // never true in practice; keeps the chains live
 }
 
 __global__ void __launch_bounds__(128) k_probe_fq_mul(Fq* io, int iters) {

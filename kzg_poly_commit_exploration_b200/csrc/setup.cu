@@ -376,15 +376,16 @@ uint64_t fixed_table_bytes(uint64_t n_points, int c) {
 
 // Window of the fixed-base table when the caller does not name one: blob throughput is ~ 1 / W(c) and random
 // 96-byte reads cost the same over 100 GiB as over 1 GiB, so the widest window whose table (plus the
-// transient folded copy) fits the memory budget wins.  Budget = option "fixed_table_max_bytes", else 60 % of the
+// transient folded copy) fits the memory budget wins.  Budget = option "fixed_table_max_bytes", else 66 % of the
 // memory that is free right now (cudaMemGetInfo): the rest stays for the batch scratch (~8 GiB at 2048 rows of 4096)
-// and for other tenants of the device.  n = 4096 on an empty B200: c = 15 (102 GiB); with 64 GiB free: c = 14 (51 GiB).
+// and for other tenants of the device.  n = 4096 on an empty B200 (178 GiB free): c = 15 (102 GiB); with 100 GiB free:
+// c = 14 (57 GiB); with 50 GiB free: c = 13 (30 GiB).
 int auto_fixed_window(kzg_ctx* ctx, uint64_t n_points) {
   size_t free_b = 0, total_b = 0;
   uint64_t budget = ctx->opt_fixed_table_max_bytes > 0 ? (uint64_t)ctx->opt_fixed_table_max_bytes : 0;
   if (!budget) {
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 10; }
-    budget = (uint64_t)((double)free_b * 0.60);
+    budget = (uint64_t)((double)free_b * 0.66);
   }
   int best = 2;
   for (int c = 2; c <= 15; c++)

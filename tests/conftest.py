@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# before anything initialises CUDA: enough hardware queues for groups whose members SHARE a device (tests/test_gpu_group.py),
+# where a spinning exchange kernel must never sit in front of the other member's kernels (see engine_one.cu)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")):
     if p not in sys.path:

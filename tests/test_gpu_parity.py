@@ -873,14 +873,14 @@ def test_zero_polynomial_builds_no_table(native):
 
 def test_fixed_window_from_memory_budget(native):
     """prepare_fixed(window 0) takes the widest window whose table fits the budget (option fixed_table_max_bytes, else
-    60 % of the free device memory): results are the same whatever window is picked"""
+    66 % of the free device memory): results are the same whatever window is picked"""
     c = native.Context(0)
     n = 256
     st = c.setup_generate(SECRET, n)
     coeffs = util.scalar_stream_bytes(0xE1, 3 * n)
     picked = []
     outs = []
-    for budget in (1 << 20, 40 << 20, 3 << 30):
+    for budget in (8 << 20, 40 << 20, 3 << 30):
         c.set_option("fixed_table_max_bytes", budget)
         st.prepare_fixed(n, 0)
         plan = st.fixed_plan()
