@@ -47,7 +47,7 @@ struct kzg_ctx {
   int opt_msm_window = 0;              // 0 = auto
   int opt_fixed_window = 0;            // 0 = auto: the widest window whose table fits the memory budget (setup.cu auto_fixed_window)
   int64_t opt_fixed_table_max_bytes = 0;   // budget of that choice; 0 = 66 % of the device memory free at the time
-  int opt_msm_sort = 0;                // bucket sort of the MSM entries: 0 = counting sort (count / scan / scatter), 1 = cub radix sort
+  int opt_msm_sort = -1;               // bucket sort of the MSM entries: 0 = counting sort (count / scan / scatter), 1 = cub radix sort, -1 = by size
   int opt_reduce_chunk = 16;
   int opt_heavy_cap = 1024;
   int opt_acc_split = -1;              // log2(threads per bucket), -1 = auto

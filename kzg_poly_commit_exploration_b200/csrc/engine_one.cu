@@ -505,9 +505,12 @@ int32_t reserve_call(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint
   DeviceGuard g(ctx->device);
   kzg_ctx* lane; int lane_index; kzg_ctx::Pending* q;
   KZG_TRY(pending_slot(ctx, n, host, &lane, &lane_index, &q));
-  if (n == 0 || lane->reserved_n >= n) return KZG_OK;
-  if (!s->msm_tab && !(s->fix_tab && n <= s->fix_n)) KZG_TRY(ensure_msm_table(ctx, s));
-  KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n == 0) return KZG_OK;
+  if (!s->msm_tab && !(s->fix_tab && n <= s->fix_n)) {      // a table build allocates too: never leave it to the submit
+    KZG_TRY(ensure_msm_table(ctx, s));
+    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (lane->reserved_n >= n) return KZG_OK;
   const uint8_t* sc = reinterpret_cast<const uint8_t*>(scalars);
   if (host) {      // whatever the staging buffer holds are valid scalars (any 32 bytes are): the run only sizes the arenas
     KZG_CUDA_OK(ctx, cudaMemsetAsync(q->scalars, 0x5a, n * 32, lane->stream));

@@ -274,7 +274,11 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   uint32_t* heavy_list = heavy_count + 1;
 
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-  if (ctx->opt_msm_sort == 0) {
+  // measured (profiles/sweep_sort_r02.txt): the atomics of the counting sort cost 0.47 ms at 16.8 M entries against 0.37 ms
+  // for recode + radix sort + bounds, but its three launches win below ~2^22 entries (n = 2^17, four lanes: 1.027 -> 1.002 ms;
+  // n = 2^14: 0.354 -> 0.336 ms)
+  const bool counting = ctx->opt_msm_sort == 0 || (ctx->opt_msm_sort < 0 && total <= (1ull << 22));
+  if (counting) {
     // counting sort: count -> scan -> scatter (see above); count[] and cursor[] share one small arena
     void* cc;
     KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)half * 2 + 8) * 4, &cc));

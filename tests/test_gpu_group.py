@@ -138,6 +138,7 @@ def test_group_import_roundtrip(group, ctx):
 
 def test_group_replicated_blob_batch(group, ctx):
     n, blobs = 512, 1031                                  # > tree_min_rows rows on some members, ragged split
+    group.set_option("setup_layout", 0)
     sg = group.setup_generate(SECRET, n)                  # auto layout: replicated
     s1 = ctx.setup_generate(SECRET, n)
     sg.prepare_fixed(n, 10)

@@ -362,13 +362,17 @@ def test_commit_adversarial_scalars(ctx, setup8k, kind):
         ints = [v if i % 2 == 0 else O.R - v for i in range(n)]
     got = ctx.msm_g1(setup8k, util.from_ints(ints))
     assert got == O.g1_compress(O.commit_known_secret(ints, S))
-    # the same through the affine halving rounds of msm_tree.cu (doublings, cancellations, odd runs, empty buckets)
-    for rounds in (1, 4):
-        ctx.set_option("msm_tree_rounds", rounds)
-        try:
-            assert ctx.msm_g1(setup8k, util.from_ints(ints)) == got, rounds
-        finally:
-            ctx.set_option("msm_tree_rounds", -1)
+    # the same through the affine halving rounds of msm_tree.cu (doublings, cancellations, odd runs, empty buckets),
+    # with the entries bucketed by the counting sort (atomics: arbitrary order inside a bucket) and by the radix sort
+    for sort_mode in (0, 1):
+        for rounds in (0, 1, 4):
+            ctx.set_option("msm_tree_rounds", rounds)
+            ctx.set_option("msm_sort", sort_mode)
+            try:
+                assert ctx.msm_g1(setup8k, util.from_ints(ints)) == got, (sort_mode, rounds)
+            finally:
+                ctx.set_option("msm_tree_rounds", -1)
+                ctx.set_option("msm_sort", -1)
 
 
 @pytest.mark.parametrize("c", [4, 7, 11, 13, 16, 17, 19])
