@@ -17,7 +17,7 @@ enum ScratchSlot {
   SCR_BUCKET_START, SCR_BUCKETS, SCR_RED_A, SCR_RED_B, SCR_HEAVY,
   SCR_XYZZ_TMP, SCR_PREFIX, SCR_QUOT, SCR_SEG, SCR_OUT, SCR_MISC, SCR_FR_A, SCR_FR_B,
   SCR_BATCH_PTS, SCR_BATCH_AFF, SCR_PARTIALS, SCR_HEAVY_PARTS,
-  SCR_TREE_A, SCR_TREE_B, SCR_TREE_PREFIX, SCR_TREE_TOT, SCR_TREE_SEG, SCR_TREE_IOTA,
+  SCR_TREE_A, SCR_TREE_B, SCR_TREE_PREFIX, SCR_TREE_TOT, SCR_TREE_SEG, SCR_TREE_IOTA, SCR_ORDER,
   SCR_COUNT
 };
 
@@ -48,6 +48,7 @@ struct kzg_ctx {
   int opt_fixed_window = 0;            // 0 = auto: the widest window whose table fits the memory budget (setup.cu auto_fixed_window)
   int64_t opt_fixed_table_max_bytes = 0;   // budget of that choice; 0 = 66 % of the device memory free at the time
   int opt_msm_sort = -1;               // bucket sort of the MSM entries: 0 = counting sort (count / scan / scatter), 1 = cub radix sort, -1 = by size
+  int opt_acc_order = 1;               // hand the buckets to k_bucket_acc sorted by length (k_bucket_order)
   int opt_reduce_chunk = 16;
   int opt_heavy_cap = 1024;
   int opt_acc_split = -1;              // log2(threads per bucket), -1 = auto
