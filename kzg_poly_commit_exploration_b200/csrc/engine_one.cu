@@ -313,6 +313,7 @@ uint64_t one_setup_len(const kzg_setup* s) { return s ? s->n : 0; }
 
 // ---- G2 half of SetupArtifact (src/trusted_setup.rs:31-35, 64-72) ----------------------------
 static int32_t setup_g2_alloc(kzg_ctx* ctx, kzg_setup* s, uint64_t count) {
+  if (s->g2_c96 && s->g2_n == count) return KZG_OK;          // regenerated in place: no free / malloc (both synchronise the device)
   if (s->g2_c96) { cudaFree(s->g2_c96); s->g2_c96 = nullptr; s->g2_n = 0; }
   if (count == 0) return KZG_OK;
   if (cudaMalloc(&s->g2_c96, count * 96) != cudaSuccess) { cudaGetLastError(); return fail(ctx, KZG_E_NOMEM, "cudaMalloc(g2)"); }
