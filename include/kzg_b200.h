@@ -90,6 +90,11 @@ float kzg_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which);
 /* CUDA-event stopwatch on the ctx stream (bench.py times its K-step region with it) */
 int32_t kzg_ctx_timer_start(kzg_ctx* ctx);
 int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms);
+/* Page-locked host memory for the buffers handed to the host-pointer calls: copies from it are asynchronous and run at
+ * the full PCIe rate (a pageable 32 MiB scalar vector costs several ms of staging per call).  Plain malloc'd memory works
+ * everywhere, this is the fast path; a Rust / C++ host needs no CUDA headers for it. */
+void* kzg_host_alloc(size_t bytes);
+void kzg_host_free(void* p);
 /* tuning: window bits for the bucket MSM (0 = auto) and for the fixed-base batch tables */
 int32_t kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value);
 

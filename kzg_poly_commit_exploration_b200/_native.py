@@ -28,6 +28,8 @@ SIGNATURES = {
     "kzg_ctx_destroy": (None, [_vp]),
     "kzg_last_error": (C.c_char_p, [_vp]),
     "kzg_status_string": (C.c_char_p, [_i32]),
+    "kzg_host_alloc": (_vp, [C.c_size_t]),
+    "kzg_host_free": (None, [_vp]),
     "kzg_ctx_sync": (_i32, [_vp]),
     "kzg_ctx_launch_count": (_u64, [_vp]),
     "kzg_ctx_stream": (_vp, [_vp]),

@@ -305,6 +305,16 @@ void kzg_ctx_destroy(kzg_ctx* ctx) {
 
 const char* kzg_last_error(const kzg_ctx* ctx) { return one_last_error(ctx); }
 
+void* kzg_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void kzg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int32_t kzg_ctx_sync(kzg_ctx* ctx) {
   if (!ctx) return KZG_E_BAD_ARG;
   if (!is_group(ctx)) return one_ctx_sync(ctx);
