@@ -224,6 +224,8 @@ int32_t one_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "fixed_window_bits") ctx->opt_fixed_window = (int)value;
   else if (n == "msm_sort") ctx->opt_msm_sort = (int)value;
   else if (n == "acc_order") ctx->opt_acc_order = (int)value;
+  else if (n == "tree_lean") ctx->opt_tree_lean = (int)value;
+  else if (n == "tree_lean_r1") ctx->opt_tree_lean_r1 = (int)value;
   else if (n == "reduce_chunk") ctx->opt_reduce_chunk = (int)value;
   else if (n == "acc_split") ctx->opt_acc_split = (int)value;
   else if (n == "acc_min_entries") ctx->opt_acc_min_entries = (int)std::max<int64_t>(1, value);
@@ -448,7 +450,7 @@ int32_t one_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32
 // the bucket reduction: a few hundred warps for ~0.6 ms); two lanes are worth 13 % at n = 2^20 and 30 % at n = 2^17, four 18 % and 44 %.
 void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
   dst->opt_msm_window = src->opt_msm_window; dst->opt_fixed_window = src->opt_fixed_window;
-  dst->opt_reduce_chunk = src->opt_reduce_chunk; dst->opt_msm_sort = src->opt_msm_sort; dst->opt_acc_order = src->opt_acc_order; dst->opt_heavy_cap = src->opt_heavy_cap; dst->opt_acc_split = src->opt_acc_split;
+  dst->opt_reduce_chunk = src->opt_reduce_chunk; dst->opt_msm_sort = src->opt_msm_sort; dst->opt_acc_order = src->opt_acc_order; dst->opt_tree_lean = src->opt_tree_lean; dst->opt_tree_lean_r1 = src->opt_tree_lean_r1; dst->opt_heavy_cap = src->opt_heavy_cap; dst->opt_acc_split = src->opt_acc_split;
   dst->opt_tree_min_rows = src->opt_tree_min_rows; dst->opt_tree_chunk_rows = src->opt_tree_chunk_rows;
   dst->opt_tree_min_pairs = src->opt_tree_min_pairs; dst->opt_inv_top_fan = src->opt_inv_top_fan; dst->opt_inv_top = src->opt_inv_top;
   dst->opt_msm_tree_rounds = src->opt_msm_tree_rounds; dst->opt_acc_min_entries = src->opt_acc_min_entries;

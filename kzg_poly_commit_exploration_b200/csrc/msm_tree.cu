@@ -156,7 +156,7 @@ template <bool R1>
 __global__ void __launch_bounds__(128)
 k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
           const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
-          const Fq* __restrict__ prefix, const Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
+          const Fq* __restrict__ prefix, Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint32_t NP = __ldg(seg_out + M);
@@ -191,8 +191,93 @@ k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_
   }
 }
 
+// ---- the same additions with fewer registers, for more warps per scheduler ----------------------------------------
+// k_seg_add keeps both points of a pair in registers (116-126 registers: 4 blocks = 16 warps per SM), and ncu shows the
+// multiplier pipe only 73-80 % busy there, the rest being fixed-latency dependency stalls that four warps per scheduler
+// cannot cover (profiles/prof_seg_add_*_summary.txt).  Here every coordinate is (re)loaded right where it is consumed —
+// the lines sit in L1 — so the loop lives in 80 / 96 registers (6 / 5 blocks per SM, a few words of spill), and the rare
+// cases (an infinity operand, a doubling, a cancellation) run out of line.
+__device__ __noinline__ void pair_add_rare(G1Affine* out, const G1Affine* p1, bool n1, const G1Affine* p2, bool n2,
+                                           const Fq* dinvp) {
+  G1Affine a, b, o;
+  Fq dinv; ld_fq_plain(dinv, dinvp);
+  ld_point(a, p1, n1);
+  ld_point(b, p2, n2);
+  pair_add(o, a, b, dinv);
+  st_fq(&out->x, o.x); st_fq(&out->y, o.y);
+}
+
+template <bool R1, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_seg_add_lean(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
+               const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
+               const Fq* __restrict__ prefix, Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t NP = __ldg(seg_out + M);
+  const uint64_t p0 = t * K;
+  if (p0 >= NP) return;
+  const int kmax = (int)min((uint64_t)K, (uint64_t)NP - p0);
+  Fq inv; ld_fq_plain(inv, tot_inv + t);
+  uint32_t b = bucket_of(seg_out, M, (uint32_t)(p0 + kmax - 1));
+#pragma unroll 1
+  for (int k = kmax - 1; k >= 0; k--) {
+    const uint32_t p = (uint32_t)p0 + k;
+    while (__ldg(seg_out + b) > p) b--;            // the bucket of p: positions are walked downwards
+    const PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p);
+    Fq d, dinv;
+    bool rare = r.p2 == nullptr;
+    if (!rare) {
+      Fq x1; ld_fq_plain(x1, &r.p1->x); ld_fq_plain(d, &r.p2->x);
+      rare = is_zero(x1) || is_zero(d);            // x = 0 may be the infinity marker
+      sub(d, d, x1);
+      rare = rare || is_zero(d);                   // doubling or cancellation
+    }
+    if (rare) pair_den(d, r.p1, r.n1, r.p2, r.n2);  // the same case analysis k_seg_den ran
+    { Fq pf; ld_fq_plain(pf, prefix + (size_t)k * T + t); mul(dinv, inv, pf); }
+    mul(inv, inv, d);
+    if (rare) {
+      st_fq(tot_inv + t, dinv);                    // this thread's own slot: read once above, free since
+      pair_add_rare(out + p, r.p1, r.n1, r.p2, r.n2, tot_inv + t);
+      continue;
+    }
+    Fq lam;
+    {
+      Fq y1, y2; ld_fq_plain(y1, &r.p1->y); ld_fq_plain(y2, &r.p2->y);
+      if (R1) { Fq m; neg(m, y1); if (r.n1) y1 = m; neg(m, y2); if (r.n2) y2 = m; }
+      sub(y2, y2, y1); mul(lam, y2, dinv);
+    }
+    Fq x3;
+    sqr(x3, lam);
+    { Fq x; ld_fq_plain(x, &r.p1->x); sub(x3, x3, x); ld_fq_plain(x, &r.p2->x); sub(x3, x3, x); }
+    st_fq(&out[p].x, x3);
+    {
+      Fq x; ld_fq_plain(x, &r.p1->x); sub(x3, x, x3); mul(x3, lam, x3);
+      ld_fq_plain(x, &r.p1->y);
+      if (R1) { Fq m; neg(m, x); if (r.n1) x = m; }
+      sub(x3, x3, x);
+    }
+    st_fq(&out[p].y, x3);
+  }
+}
 
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// Which addition kernel a round runs (options tree_lean / tree_lean_r1; measured at n = 2^20, profiles/sweep_lean_r02.txt):
+// the reloading variant at the SAME 4 blocks per SM is 0.5-0.8 % faster on the dense rounds (6.46 -> 6.40 ms alone,
+// 5.40 -> 5.36 ms with four lanes; on round 1 another 6.39 -> 6.31 / 5.37 -> 5.35 ms) and is the default; at 5 or 6 blocks
+// per SM it is SLOWER (dense rounds 5.40 / 5.46 ms, round 1 5.53 / 5.64 ms): more warps do not help, the multiplier pipe is the bound, not latency.  Capping the
+// residency of these kernels with idle shared memory so that another lane's denominator gather could run beside them
+// costs 6 % (profiles/sweep_carve_r02.txt): not kept.
+template <bool R1>
+static void launch_seg_add(kzg_ctx* ctx, unsigned grid, const uint32_t* seg_in, const uint32_t* so, uint32_t M, const uint32_t* vals,
+                           const G1Affine* src, uint64_t T, int K, const Fq* prefix, Fq* tot, G1Affine* out) {
+  const int lean = R1 ? ctx->opt_tree_lean_r1 : ctx->opt_tree_lean;
+  if (lean == 6) k_seg_add_lean<R1, 6><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
+  else if (lean == 5) k_seg_add_lean<R1, 5><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
+  else if (lean == 4) k_seg_add_lean<R1, 4><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
+  else k_seg_add<R1><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
+}
 
 int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const char* tab_pitched,
                         uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
@@ -231,10 +316,12 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   for (int r = 0; r < rounds; r++) {
     bound = halve(bound);
     // pairs per thread: the blocks of a launch are identical and run in lockstep, so a launch costs WHOLE waves of
-    // (4 blocks per SM) x K pair-times — 3.47 waves cost 4.  Pick the K <= 16 that fills the last wave.
+    // (4 - 6 blocks per SM) x K pair-times — 3.47 waves cost 4.  Pick the K <= 16 that fills the last wave.
     int K = ST_K;
     {
-      const double per_slot = (double)bound * 1.004 / ((double)ctx->sm_count * 4 * 128);
+      const int lean = r == 0 ? ctx->opt_tree_lean_r1 : ctx->opt_tree_lean;
+      const int bps = lean >= 4 && lean <= 6 ? lean : 4;                 // resident blocks per SM of this round's addition kernel
+      const double per_slot = (double)bound * 1.004 / ((double)ctx->sm_count * bps * 128);
       int waves = (int)((per_slot + ST_K - 1e-9) / ST_K); if (waves < 1) waves = 1;
       K = (int)(per_slot / waves + 0.999999);
       if (K < 8) K = 8;
@@ -250,9 +337,9 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
     KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
     if (r == 0) {
       KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
-      k_seg_add<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot, out);
+      launch_seg_add<true>(ctx, blocks_for(T, 128), seg_in, so, M, vals_dev, src, T, K, prefix, tot, out);
       KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
-    } else k_seg_add<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, K, prefix, tot, out);
+    } else launch_seg_add<false>(ctx, blocks_for(T, 128), seg_in, so, M, nullptr, src, T, K, prefix, tot, out);
     KZG_LAUNCHED(ctx);
     seg_in = so; src = out;
   }
