@@ -77,7 +77,7 @@ struct GroupTicket {
 
 struct GroupState {
   std::vector<std::unique_ptr<Worker>> workers;     // workers[g - 1] serves member g
-  GroupTicket tickets[KZG_MAX_LANES];
+  GroupTicket tickets[KZG_MAX_INFLIGHT];
 };
 
 inline bool is_group(const kzg_ctx* ctx) { return ctx && !ctx->members.empty(); }
@@ -198,13 +198,20 @@ void group_destroy(kzg_ctx* head) {
   one_ctx_destroy(head);
 }
 
+// launch what the members still hold back for fusing
+void group_flush(kzg_ctx* head) {
+  bool any = false;
+  for (kzg_ctx* m : head->members) any = any || m->open_group.count > 0;
+  if (any) for_members(head, [](int, kzg_ctx* m) { return flush_submitted(m); });
+}
+
 // ---- one MSM on a group --------------------------------------------------------------------------------------------
 // `scalars` is a host buffer (host == true) or a device pointer on any member device; *ticket = the head's ticket
 int32_t group_msm_submit(kzg_ctx* head, const kzg_setup* S, const void* scalars, uint64_t n, bool host, int32_t* ticket) {
   if (n > S->n) return fail(head, KZG_E_DEGREE_TOO_HIGH, kzg_status_string(KZG_E_DEGREE_TOO_HIGH));
   const int G = group_size(head);
-  const int L = std::min(KZG_MAX_LANES, std::max(1, head->lanes_in_use ? head->lanes_in_use : head->opt_lanes));
-  GroupTicket& T = gs(head)->tickets[head->next_ticket % (uint32_t)L];
+  const uint32_t F = queue_capacity(head);              // tickets that can be out at once: lanes x fused calls
+  GroupTicket& T = gs(head)->tickets[head->next_ticket % F];
   if (T.busy) return fail(head, KZG_E_BAD_ARG, "every lane has a call in flight: wait for the oldest ticket first");
   for (int g = 0; g < G; g++) T.member_ticket[g] = -1;
   // a replicated setup, or a sum that lives entirely in member 0's range: that device alone, no exchange
@@ -237,10 +244,12 @@ int32_t group_msm_submit(kzg_ctx* head, const kzg_setup* S, const void* scalars,
 
 int32_t group_msm_wait(kzg_ctx* head, int32_t ticket, uint8_t out_c48[48]) {
   if (ticket < 0) return KZG_E_BAD_ARG;
-  const int L = std::max(1, head->lanes_in_use);
-  GroupTicket& T = gs(head)->tickets[(uint32_t)ticket % (uint32_t)L];
+  GroupTicket& T = gs(head)->tickets[(uint32_t)ticket % queue_capacity(head)];
   if (!T.busy || T.member_ticket[0] != ticket) return fail(head, KZG_E_BAD_ARG, "no call in flight under this ticket");
   T.busy = false;
+  // calls still staged for fusing (option msm_coalesce): EVERY member launches its part before anybody waits — a member's
+  // exchange kernel spins until all the others have published
+  group_flush(head);
   int32_t first_err = KZG_OK;
   uint8_t sink[48];
   for (int g = group_size(head) - 1; g >= 0; g--) {      // every member computed the fold; member 0's copy is the answer
@@ -318,6 +327,7 @@ void kzg_host_free(void* p) {
 int32_t kzg_ctx_sync(kzg_ctx* ctx) {
   if (!ctx) return KZG_E_BAD_ARG;
   if (!is_group(ctx)) return one_ctx_sync(ctx);
+  group_flush(ctx);
   for (kzg_ctx* m : ctx->members) {
     int32_t st = one_ctx_sync(m);
     if (st != KZG_OK) { if (m != ctx) ctx->err = m->err; return st; }
@@ -348,6 +358,7 @@ int32_t kzg_ctx_timer_start(kzg_ctx* ctx) {
 int32_t kzg_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
   if (!ctx || !ms) return KZG_E_BAD_ARG;
   if (!is_group(ctx)) return one_ctx_timer_stop(ctx, ms);
+  group_flush(ctx);
   float worst = 0.f;
   for (kzg_ctx* m : ctx->members) {
     float t = 0.f;

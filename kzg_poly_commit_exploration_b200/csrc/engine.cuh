@@ -23,8 +23,10 @@ enum ScratchSlot {
 
 constexpr int KZG_MAX_PEERS = 32;
 constexpr int KZG_MAX_LANES = 4;      // calls in flight per context (kzg_msm_g1_submit*): one lane (streams + scratch) each
-constexpr int KZG_P2P_DEPTH = 2 * KZG_MAX_LANES;   // mailbox slots per peer: with at most L calls in flight per rank, call
-                                     // k + L may overwrite the slot of call k - L, which every rank has finished reading (msm_tail.cu)
+constexpr int KZG_MAX_COALESCE = 4;   // submitted calls fused into one bucket problem (option msm_coalesce, msm_bucket_multi)
+constexpr int KZG_MAX_INFLIGHT = KZG_MAX_LANES * KZG_MAX_COALESCE;   // tickets that can be out at once
+constexpr int KZG_P2P_DEPTH = 2 * KZG_MAX_INFLIGHT;   // mailbox slots per peer: with at most F calls in flight per rank, call
+                                     // k + F may overwrite the slot of call k - F, which every rank has finished reading (msm_tail.cu)
 }  // namespace kzg
 
 struct kzg_ctx {
@@ -77,10 +79,28 @@ struct kzg_ctx {
     uint8_t* out_host = nullptr;               // pinned, 64 bytes (result + status of a sharded call)
     bool sharded = false;
     cudaEvent_t copied = nullptr, done = nullptr;
-    int32_t status = 0;
+    int32_t status = 0;                        // failure of the launch that carried this call (reported by the wait)
     bool busy = false;
-  } pending[kzg::KZG_MAX_LANES];
+    bool launched = false;                     // false: still in the open group (msm_coalesce), nothing issued yet
+    bool host = false;
+    uint32_t ticket = 0;
+    int lane_index = 0;
+    const uint8_t* dev_scalars = nullptr;      // what the launch reads: the staging buffer or the caller's device pointer
+  } pending[kzg::KZG_MAX_INFLIGHT];            // ticket t lives in slot t mod (lanes x coalesce)
   uint32_t next_ticket = 0;
+  // Calls fused into one bucket problem (option msm_coalesce = B > 1, msm.cu msm_bucket_multi): a submit only stages its
+  // scalars and joins the OPEN group; the group is launched on the next lane when it holds B calls, when a call with
+  // another setup / length / kind arrives, or when somebody waits for (or synchronises with) one of its tickets.
+  int opt_msm_coalesce = 1;
+  int coalesce_in_use = 0;                     // latched with lanes_in_use by the first submit
+  struct OpenGroup {
+    int count = 0;
+    uint32_t first_ticket = 0;
+    const kzg_setup* s = nullptr;
+    uint64_t n = 0;
+    bool sharded = false;
+  } open_group;
+  uint32_t groups_launched = 0;                // group g runs on lane g mod L
   int opt_setup_tree_min = 1 << 18;    // setup generation: affine-tree path from this many points on (0 = never)
   int opt_lanes = 4;                   // calls in flight (1 .. KZG_MAX_LANES); fixed once the first ticket is out
   int lanes_in_use = 0;                // opt_lanes latched by the first submit
@@ -200,8 +220,13 @@ int32_t validate_g2_points(kzg_ctx* ctx, const uint8_t* in_c96_dev, uint64_t n, 
 // result_dev: one G1Xyzz (device).  Uses s->msm_tab (built on demand).
 int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
                    G1Xyzz* result_dev);
+// B sums of n scalars each over the same bases as ONE bucket problem (B <= KZG_MAX_COALESCE); results_dev: B G1Xyzz
+int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const* scalars_dev, int B, uint64_t n,
+                         G1Xyzz* results_dev);
 // sum_b (b+1) * A_b, A_b = sum_k parts[b*T + k] with T = 2^logT partials per bucket (msm_tail.cu)
 int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, G1Xyzz* result_dev);
+// the same for B consecutive bucket sets of M <= 32768 buckets each, one launch set (blockIdx.y = set); results_dev: B G1Xyzz
+int32_t reduce_buckets_multi(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, int B, G1Xyzz* results_dev);
 // out_dev[0..count) = infinity
 int32_t set_infinity(kzg_ctx* ctx, G1Xyzz* out_dev, uint32_t count);
 // sum `count` XYZZ points (device) into out_dev[0]
@@ -216,9 +241,10 @@ struct PeerMailbox {
   uint32_t dead[KZG_MAX_PEERS];                  // != 0: that rank gave up (timed out) in the call of this number — sticky
 };
 struct PeerTable { PeerMailbox* box[KZG_MAX_PEERS]; };
-// `ctx` supplies the stream, `owner` the mailboxes; seq = number of this collective call (same on every rank)
+// `ctx` supplies the stream, `owner` the mailboxes; seq = number of this collective call (same on every rank).
+// calls > 1: mine_dev[k] belongs to collective call seq + k, its output and status word sit k * out_stride bytes on.
 int32_t exchange_combine(kzg_ctx* ctx, const kzg_ctx* owner, uint32_t seq, const G1Xyzz* mine_dev, uint8_t* out_c48_dev,
-                         uint32_t* status_dev);
+                         uint32_t* status_dev, int calls = 1, uint32_t out_stride = 0);
 
 // ---- batch.cu (K5) ---------------------------------------------------------------------------
 // blobs MSMs of n scalars each against the fixed-base table; out: blobs XYZZ
@@ -294,6 +320,10 @@ int32_t one_probe_imad_peak(kzg_ctx* ctx, double* wide_mac_per_s);
 int32_t one_probe_fq_mul(kzg_ctx* ctx, double* fq_mul_per_s);
 int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host, bool sharded, int32_t* ticket);
 void copy_options(kzg_ctx* dst, const kzg_ctx* src);
+// launch the calls a context still holds back for fusing (option msm_coalesce); their failures are reported by their waits
+int32_t flush_submitted(kzg_ctx* ctx);
+// tickets that can be out at once (lanes x fused calls); fixes both numbers if no call has been submitted yet
+uint32_t queue_capacity(kzg_ctx* ctx);
 int32_t reserve_call(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint64_t n, bool host);
 // stages the coefficients, runs the scan, applies divide_by_root's error rules; *q_dev = trimmed quotient on the device
 int32_t quotient_core(kzg_ctx* ctx, const uint8_t* coeffs_le32, uint64_t n, const uint8_t z_le[32], const uint8_t* y_le,

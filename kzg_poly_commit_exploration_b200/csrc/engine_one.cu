@@ -181,6 +181,7 @@ const char* one_last_error(const kzg_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int32_t one_ctx_sync(kzg_ctx* ctx) {
   DeviceGuard g(ctx->device);
+  flush_submitted(ctx);
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   for (int l = 1; l < KZG_MAX_LANES; l++) if (ctx->lane[l]) KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->lane[l]->stream));
   update_timers(ctx);
@@ -195,6 +196,7 @@ int32_t one_ctx_timer_start(kzg_ctx* ctx) {
 
 int32_t one_ctx_timer_stop(kzg_ctx* ctx, float* ms) {
   DeviceGuard g(ctx->device);
+  flush_submitted(ctx);
   for (int l = 1; l < KZG_MAX_LANES; l++) {     // the interval ends when EVERY lane is done
     if (!ctx->lane[l]) continue;
     KZG_CUDA_OK(ctx, cudaEventRecord(ctx->lane[l]->ev_t[1], ctx->lane[l]->stream));
@@ -245,6 +247,10 @@ int32_t one_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "lanes") {
     if (ctx->lanes_in_use) return fail(ctx, KZG_E_BAD_ARG, "the number of lanes is fixed once a call has been submitted");
     ctx->opt_lanes = (int)std::min<int64_t>(KZG_MAX_LANES, std::max<int64_t>(1, value));
+  }
+  else if (n == "msm_coalesce") {
+    if (ctx->lanes_in_use) return fail(ctx, KZG_E_BAD_ARG, "the number of fused calls is fixed once a call has been submitted");
+    ctx->opt_msm_coalesce = (int)std::min<int64_t>(KZG_MAX_COALESCE, std::max<int64_t>(1, value));
   }
   else if (n == "heavy_cap") ctx->opt_heavy_cap = (int)std::max<int64_t>(1, value);
   else return fail(ctx, KZG_E_BAD_ARG, "unknown option");
@@ -458,9 +464,18 @@ void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
   dst->opt_setup_tree_min = src->opt_setup_tree_min; dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_acc_minblocks = src->opt_acc_minblocks;
 }
 
-static int32_t lane_of(kzg_ctx* ctx, uint32_t ticket, kzg_ctx** lane) {
-  if (!ctx->lanes_in_use) ctx->lanes_in_use = std::min(KZG_MAX_LANES, std::max(1, ctx->opt_lanes));
-  const int l = (int)(ticket % (uint32_t)ctx->lanes_in_use);
+static void latch_queue(kzg_ctx* ctx) {
+  if (ctx->lanes_in_use) return;
+  ctx->lanes_in_use = std::min(KZG_MAX_LANES, std::max(1, ctx->opt_lanes));
+  ctx->coalesce_in_use = std::min(KZG_MAX_COALESCE, std::max(1, ctx->opt_msm_coalesce));
+  // members of a group that share a device allocate in a phase of their own before anything is launched (reserve_call):
+  // a deferred launch would allocate later, behind a peer's spinning exchange kernel
+  if (ctx->group_head && ctx->group_head->group_shares_devices) ctx->coalesce_in_use = 1;
+}
+static inline uint32_t queue_slots(const kzg_ctx* ctx) { return (uint32_t)(ctx->lanes_in_use * ctx->coalesce_in_use); }
+
+// lane l of the context (l = 0: the context itself), created on first use
+static int32_t lane_at(kzg_ctx* ctx, int l, kzg_ctx** lane) {
   *lane = ctx;
   if (l == 0) return KZG_OK;
   if (!ctx->lane[l]) {
@@ -472,13 +487,14 @@ static int32_t lane_of(kzg_ctx* ctx, uint32_t ticket, kzg_ctx** lane) {
   return KZG_OK;
 }
 
-// lane + result slot + staging buffer of the next ticket, allocated on first use
+// lane of the group the next ticket joins + result slot + staging buffer of that ticket, allocated on first use
 static int32_t pending_slot(kzg_ctx* ctx, uint64_t n, bool host, kzg_ctx** lane_out, int* lane_index_out, kzg_ctx::Pending** q_out) {
+  latch_queue(ctx);
   const uint32_t t = ctx->next_ticket;
+  const int lane_index = (int)(ctx->groups_launched % (uint32_t)ctx->lanes_in_use);
   kzg_ctx* lane;
-  KZG_TRY(lane_of(ctx, t, &lane));
-  const int lane_index = (int)(t % (uint32_t)ctx->lanes_in_use);
-  kzg_ctx::Pending& q = ctx->pending[lane_index];
+  KZG_TRY(lane_at(ctx, lane_index, &lane));
+  kzg_ctx::Pending& q = ctx->pending[t % queue_slots(ctx)];
   if (q.busy) return fail(ctx, KZG_E_BAD_ARG, "every lane has a call in flight: wait for the oldest ticket first");
   if (!q.copied) {
     KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&q.copied, cudaEventDisableTiming));
@@ -520,12 +536,82 @@ int32_t reserve_call(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint
     KZG_CUDA_OK(ctx, cudaMemsetAsync(q->scalars, 0x5a, n * 32, lane->stream));
     sc = reinterpret_cast<const uint8_t*>(q->scalars);
   }
-  int32_t st = msm_any(lane, s, sc, n, reinterpret_cast<G1Xyzz*>(q->result));
-  if (st == KZG_OK) st = finalize_points(lane, reinterpret_cast<G1Xyzz*>(q->result), 1, reinterpret_cast<uint8_t*>(q->result) + 256);
+  void* r;
+  KZG_TRY(scratch_get(lane, SCR_MISC, 1024, &r));
+  int32_t st = msm_any(lane, s, sc, n, reinterpret_cast<G1Xyzz*>(r));
+  if (st == KZG_OK) st = finalize_points(lane, reinterpret_cast<G1Xyzz*>(r), 1, reinterpret_cast<uint8_t*>(q->result) + 256);
   if (st != KZG_OK) { if (lane != ctx) ctx->err = lane->err; return st; }
   KZG_CUDA_OK(ctx, cudaStreamSynchronize(lane->stream));
   lane->reserved_n = n;
   return KZG_OK;
+}
+
+// Launch the open group (1 .. B staged calls with the same setup, length and kind) on the next lane: one bucket problem
+// for all of them, then the compression (or the peer exchange) of every result and the read-backs the waits collect.
+// A failure is kept in every call of the group and reported by its wait.
+static int32_t flush_open_group(kzg_ctx* ctx) {
+  kzg_ctx::OpenGroup& og = ctx->open_group;
+  const int B = og.count;
+  if (B == 0) return KZG_OK;
+  DeviceGuard g(ctx->device);
+  const uint32_t slots = queue_slots(ctx);
+  kzg_ctx::Pending* q[KZG_MAX_COALESCE];
+  for (int k = 0; k < B; k++) q[k] = &ctx->pending[(og.first_ticket + (uint32_t)k) % slots];
+  const kzg_setup* s = og.s;
+  const uint64_t n = og.n;
+  const bool sharded = og.sharded;
+  og.count = 0;
+  const int lane_index = (int)(ctx->groups_launched % (uint32_t)ctx->lanes_in_use);
+  kzg_ctx* lane = nullptr;
+  auto run = [&]() -> int32_t {
+    KZG_TRY(lane_at(ctx, lane_index, &lane));
+    if (n && !s->msm_tab && !(s->fix_tab && n <= s->fix_n)) {      // built once, on the main lane, before any lane reads it
+      KZG_TRY(ensure_msm_table(ctx, s));
+      KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int k = 0; k < B; k++)
+      if (q[k]->host) KZG_CUDA_OK(lane, cudaStreamWaitEvent(lane->stream, q[k]->copied, 0));
+    void *r, *o;
+    KZG_TRY(scratch_get(lane, SCR_MISC, 1024, &r));                  // B <= 4 partial sums of 192 bytes
+    KZG_TRY(scratch_get(lane, SCR_OUT, 64 * KZG_MAX_COALESCE, &o));  // per call 48 compressed bytes (+ the status word of an exchange)
+    G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
+    uint8_t* out_dev = reinterpret_cast<uint8_t*>(o);
+    lane->throughput_mode = ctx->lanes_in_use > 1 || B > 1;   // several calls in flight: tuned for throughput, not for the shortest chain
+    int32_t st = KZG_OK;
+    if (B == 1 || n == 0 || (s->fix_tab && n <= s->fix_n)) {
+      for (int k = 0; k < B && st == KZG_OK; k++) st = msm_any(lane, s, q[k]->dev_scalars, n, res + k);
+    } else {
+      const uint8_t* ptrs[KZG_MAX_COALESCE];
+      for (int k = 0; k < B; k++) ptrs[k] = q[k]->dev_scalars;
+      st = msm_bucket_multi(lane, s, ptrs, B, n, res);
+    }
+    lane->throughput_mode = false;
+    KZG_TRY(st);
+    uint32_t rec = 48;
+    if (sharded) {
+      // collective calls are numbered by their own counter (every rank issues the same sequence of SHARDED calls; plain
+      // submits in between do not count); the calls of a group take consecutive numbers, one block of the kernel each
+      rec = 64;
+      KZG_TRY(exchange_combine(lane, ctx, ctx->p2p_seq + 1, res, out_dev, reinterpret_cast<uint32_t*>(out_dev + 48), B, rec));
+      ctx->p2p_seq += (uint32_t)B;
+    } else {
+      KZG_TRY(finalize_points(lane, res, (uint64_t)B, out_dev));
+    }
+    for (int k = 0; k < B; k++) {
+      KZG_CUDA_OK(lane, cudaMemcpyAsync(q[k]->out_host, out_dev + (size_t)k * rec, rec, cudaMemcpyDeviceToHost, lane->stream));
+      KZG_CUDA_OK(lane, cudaEventRecord(q[k]->done, lane->stream));
+    }
+    return KZG_OK;
+  };
+  const int32_t st = run();
+  if (st != KZG_OK) {
+    if (lane && lane != ctx) ctx->err = lane->err;
+    if (sharded) ctx->p2p_failed = true;                // the peers may already be waiting for partials that will not come
+  }
+  for (int k = 0; k < B; k++) { q[k]->launched = true; q[k]->status = st; q[k]->lane_index = lane_index; }
+  ctx->last_lane = lane_index;
+  ctx->groups_launched++;
+  return st;
 }
 
 // host == true: `scalars` is a host buffer, copied on the lane's copy stream (device pointers may live on ANY device
@@ -540,43 +626,34 @@ int32_t submit_common(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uin
     return fail(ctx, KZG_E_CUDA, "the peer exchange of this context failed earlier (a rank timed out): its sequence numbers are "
                                  "no longer in step, create the contexts again");
   DeviceGuard g(ctx->device);
+  latch_queue(ctx);
+  kzg_ctx::OpenGroup& og = ctx->open_group;
+  // a call that cannot ride with the staged ones sends them off first (their failure, if any, is theirs to report)
+  if (og.count > 0 && (og.s != s || og.n != n || og.sharded != sharded)) (void)flush_open_group(ctx);
   const uint32_t t = ctx->next_ticket;
   kzg_ctx* lane; int lane_index; kzg_ctx::Pending* qp;
   KZG_TRY(pending_slot(ctx, n, host, &lane, &lane_index, &qp));
   kzg_ctx::Pending& q = *qp;
-  if (n && !s->msm_tab && !(s->fix_tab && n <= s->fix_n)) {      // built once, on the main lane, before any lane reads it
-    KZG_TRY(ensure_msm_table(ctx, s));
-    KZG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  }
-  const uint8_t* dev_scalars = reinterpret_cast<const uint8_t*>(scalars);
+  q.dev_scalars = reinterpret_cast<const uint8_t*>(scalars);
   if (host) {
     if (n) KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.scalars, scalars, n * 32, cudaMemcpyHostToDevice, lane->copy_stream));
     KZG_CUDA_OK(ctx, cudaEventRecord(q.copied, lane->copy_stream));
-    KZG_CUDA_OK(ctx, cudaStreamWaitEvent(lane->stream, q.copied, 0));
-    dev_scalars = reinterpret_cast<const uint8_t*>(q.scalars);
+    q.dev_scalars = reinterpret_cast<const uint8_t*>(q.scalars);
   }
-  G1Xyzz* res = reinterpret_cast<G1Xyzz*>(q.result);
-  uint8_t* out_dev = reinterpret_cast<uint8_t*>(q.result) + 256;
-  lane->throughput_mode = ctx->lanes_in_use > 1;      // several calls in flight: tuned for throughput, not for the shortest chain
-  int32_t st = msm_any(lane, s, dev_scalars, n, res);
-  lane->throughput_mode = false;
-  if (st == KZG_OK) {
-    // collective calls are numbered by their own counter (every rank issues the same sequence of SHARDED calls; plain
-    // submits in between do not count)
-    if (sharded) st = exchange_combine(lane, ctx, ++ctx->p2p_seq, res, out_dev, reinterpret_cast<uint32_t*>(out_dev + 48));
-    else st = finalize_points(lane, res, 1, out_dev);
-  }
-  if (st != KZG_OK) {
-    if (lane != ctx) ctx->err = lane->err;
-    if (sharded) ctx->p2p_failed = true;              // the peers may already be waiting for a partial that will not come
-    return st;
-  }
-  KZG_CUDA_OK(ctx, cudaMemcpyAsync(q.out_host, out_dev, 64, cudaMemcpyDeviceToHost, lane->stream));
-  KZG_CUDA_OK(ctx, cudaEventRecord(q.done, lane->stream));
-  q.busy = true; q.sharded = sharded;
-  ctx->last_lane = lane_index;
-  *ticket = (int32_t)t;
+  q.busy = true; q.launched = false; q.status = KZG_OK; q.sharded = sharded; q.host = host; q.ticket = t; q.lane_index = lane_index;
+  if (og.count == 0) { og.first_ticket = t; og.s = s; og.n = n; og.sharded = sharded; }
+  og.count++;
   ctx->next_ticket = t + 1;
+  *ticket = (int32_t)t;
+  if (og.count >= ctx->coalesce_in_use) {
+    const int32_t st = flush_open_group(ctx);
+    if (st != KZG_OK) {          // this call never got a ticket: give its slot back; the earlier calls of the group report st from their waits
+      q.busy = false;
+      ctx->next_ticket = t;
+      *ticket = -1;
+      return st;
+    }
+  }
   return KZG_OK;
 }
 
@@ -593,16 +670,31 @@ int32_t one_msm_g1_sharded_submit(kzg_ctx* ctx, const kzg_setup* s, const uint8_
   return submit_common(ctx, s, scalars_le32, n, true, true, ticket);
 }
 
+uint32_t queue_capacity(kzg_ctx* ctx) { latch_queue(ctx); return queue_slots(ctx); }
+
+// launch whatever is still staged (kzg_ctx_sync, the timers, and anybody else who is about to look at the device)
+int32_t flush_submitted(kzg_ctx* ctx) {
+  if (!ctx || ctx->open_group.count == 0) return KZG_OK;
+  (void)flush_open_group(ctx);      // a failure belongs to the staged calls: their waits report it
+  return KZG_OK;
+}
+
 int32_t one_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
   if (!ctx || !out_c48 || ticket < 0) return KZG_E_BAD_ARG;
-  const uint32_t t = (uint32_t)ticket, L = (uint32_t)std::max(1, ctx->lanes_in_use);
-  kzg_ctx::Pending& q = ctx->pending[t % L];
-  if (!q.busy || ctx->next_ticket - t < 1 || ctx->next_ticket - t > L)
+  if (!ctx->lanes_in_use) return fail(ctx, KZG_E_BAD_ARG, "no call in flight under this ticket");
+  const uint32_t t = (uint32_t)ticket, F = queue_slots(ctx);
+  kzg_ctx::Pending& q = ctx->pending[t % F];
+  if (!q.busy || q.ticket != t || ctx->next_ticket - t < 1 || ctx->next_ticket - t > F)
     return fail(ctx, KZG_E_BAD_ARG, "no call in flight under this ticket");
   DeviceGuard g(ctx->device);
+  if (!q.launched) (void)flush_open_group(ctx);       // still staged: send the partial group off now
+  if (q.status != KZG_OK) {                           // the launch that carried this call failed (ctx->err has the first message)
+    q.busy = false;
+    return q.status;
+  }
   KZG_CUDA_OK(ctx, cudaEventSynchronize(q.done));
   q.busy = false;
-  ctx->last_lane = (int)(t % L);
+  ctx->last_lane = q.lane_index;
   update_timers(ctx);
   if (q.sharded) {
     uint32_t st;

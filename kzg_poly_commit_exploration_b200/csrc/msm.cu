@@ -77,10 +77,15 @@ __global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, uint64_t tota
 // order the atomics resolve: sums do not care, every addition downstream is complete, and the result is a canonical
 // encoding — bit-identical output, fewer passes: recode + 2 onesweep passes + histogram + bounds (0.37 ms at n = 2^20)
 // become three launches.
+// Several calls at once (msm_bucket_multi): blockIdx.y = call, its buckets are [call * half, (call + 1) * half).
+struct ScalarPtrs { const uint8_t* p[KZG_MAX_COALESCE]; };
+
 __global__ void __launch_bounds__(256)
-k_digit_count(const uint8_t* __restrict__ scalars, uint64_t n, int c, int W, uint32_t* __restrict__ count) {
+k_digit_count(ScalarPtrs sp, uint64_t n, int c, int W, uint32_t half, uint32_t* __restrict__ count) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint8_t* __restrict__ scalars = sp.p[blockIdx.y];
+  count += (size_t)blockIdx.y * half;
   Fr k; ld_scalar(k, scalars + i * 32);
   fr_canon_reduce(k);
   SignedDigits sd; sd.init(k, c);
@@ -121,10 +126,12 @@ k_bucket_scan(const uint32_t* __restrict__ count, uint32_t M, uint32_t* __restri
 }
 
 __global__ void __launch_bounds__(256)
-k_digit_scatter(const uint8_t* __restrict__ scalars, uint64_t n, int c, int W, uint64_t n_stride,
+k_digit_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint32_t half,
                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ vals) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint8_t* __restrict__ scalars = sp.p[blockIdx.y];
+  cursor += (size_t)blockIdx.y * half;
   Fr k; ld_scalar(k, scalars + i * 32);
   fr_canon_reduce(k);
   SignedDigits sd; sd.init(k, c);
@@ -328,11 +335,12 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
     uint32_t* count = reinterpret_cast<uint32_t*>(cc);
     uint32_t* cursor = count + half + 4;
     KZG_CUDA_OK(ctx, cudaMemsetAsync(count, 0, (size_t)half * 4, ctx->stream));
-    k_digit_count<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(scalars_dev, n, c, W, count);
+    ScalarPtrs sp = {}; sp.p[0] = scalars_dev;
+    k_digit_count<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(sp, n, c, W, half, count);
     KZG_LAUNCHED(ctx);
     k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(count, half, reinterpret_cast<uint32_t*>(st), cursor);
     KZG_LAUNCHED(ctx);
-    k_digit_scatter<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(scalars_dev, n, c, W, s->n, cursor, reinterpret_cast<uint32_t*>(vb));
+    k_digit_scatter<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(sp, n, c, W, s->n, half, cursor, reinterpret_cast<uint32_t*>(vb));
     KZG_LAUNCHED(ctx);
   } else {
     // radix path (option msm_sort = 1, kept for comparison): recode -> cub::DeviceRadixSort over c key bits -> bounds
@@ -416,6 +424,105 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
     KZG_LAUNCHED(ctx);
   }
   KZG_TRY(reduce_buckets(ctx, reinterpret_cast<G1Xyzz*>(parts), half, logT, result_dev));
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  return KZG_OK;
+}
+
+// ---- several calls as ONE bucket problem -------------------------------------------------------------------------
+// B sums over the same bases (calls that are in flight together, kzg_msm_g1_submit* with option msm_coalesce; the rows of
+// a batch of long polynomials) are a single MSM with B times the buckets: entry (call, window j, point i) goes to bucket
+// call * 2^(c-1) + |digit| - 1 and reads the SAME table entry j * n + i.  Sort, halving rounds and accumulation then run
+// once over B * W * n entries — kernels B times the size, one inversion chain per round instead of B — and only the
+// bucket reduction runs per call (one launch set, blockIdx.y = call).  At n = 2^17 (the per-GPU share of the 8-GPU MSM)
+// the kernels of a lone call are single partial waves; four calls fused run with the efficiency of n = 2^19.
+int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const* scalars_dev, int B, uint64_t n,
+                         G1Xyzz* results_dev) {
+  if (B < 1 || B > KZG_MAX_COALESCE) return fail(ctx, KZG_E_BAD_ARG, "bad number of fused calls");
+  if (B == 1) return msm_bucket(ctx, s, scalars_dev[0], n, results_dev);
+  if (n == 0) return set_infinity(ctx, results_dev, (uint32_t)B);
+  if (!s->msm_tab) return fail(ctx, KZG_E_BAD_ARG, "msm table not prepared");
+  const int c = s->msm_c, W = s->msm_w;
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t M = half * (uint32_t)B;
+  const uint64_t total = (uint64_t)W * n * (uint64_t)B;
+  if ((uint64_t)W * s->n >= (1ull << 31) || total >= (1ull << 32))
+    return fail(ctx, KZG_E_BAD_ARG, "msm too large for 31-bit table indices");
+  if (half > 32768) return fail(ctx, KZG_E_BAD_ARG, "fused calls need a window of at most 16 bits");
+
+  void *vb, *st, *hv, *cc;
+  KZG_TRY(scratch_get(ctx, SCR_VALS_B, total * 4, &vb));
+  KZG_TRY(scratch_get(ctx, SCR_BUCKET_START, ((size_t)M + 3) * 4, &st));
+  const uint32_t heavy_cap = (uint32_t)ctx->opt_heavy_cap;
+  size_t heavy_max = total / heavy_cap + 2 + 64;
+  KZG_TRY(scratch_get(ctx, SCR_HEAVY, (heavy_max + 1) * 4, &hv));
+  uint32_t* heavy_count = reinterpret_cast<uint32_t*>(hv);
+  uint32_t* heavy_list = heavy_count + 1;
+  KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)M * 2 + 8) * 4, &cc));
+  uint32_t* count = reinterpret_cast<uint32_t*>(cc);
+  uint32_t* cursor = count + M + 4;
+
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  ScalarPtrs sp = {};
+  for (int b = 0; b < B; b++) sp.p[b] = scalars_dev[b];
+  KZG_CUDA_OK(ctx, cudaMemsetAsync(count, 0, (size_t)M * 4, ctx->stream));
+  k_digit_count<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, half, count);
+  KZG_LAUNCHED(ctx);
+  k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(count, M, reinterpret_cast<uint32_t*>(st), cursor);
+  KZG_LAUNCHED(ctx);
+  k_digit_scatter<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, s->n, half, cursor,
+                                                                                 reinterpret_cast<uint32_t*>(vb));
+  KZG_LAUNCHED(ctx);
+  KZG_CUDA_OK(ctx, cudaMemsetAsync(heavy_count, 0, 4, ctx->stream));
+
+  const uint32_t* acc_start = reinterpret_cast<uint32_t*>(st);
+  const uint32_t* acc_vals = reinterpret_cast<uint32_t*>(vb);
+  const char* acc_tab = s->msm_tab;
+  uint32_t acc_pitch = MSM_TAB_PITCH;
+  uint64_t acc_entries = total;
+  int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds(total);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (rounds > 0) {
+    const G1Affine* dense = nullptr;
+    KZG_TRY(msm_tree_rounds(ctx, acc_start, acc_vals, acc_tab, M, total, rounds, &dense, &acc_start, &acc_vals, &acc_entries));
+    acc_tab = reinterpret_cast<const char*>(dense); acc_pitch = DENSE_PITCH;
+  }
+  uint32_t logT = 0;
+  if (ctx->opt_acc_split >= 0) logT = (uint32_t)ctx->opt_acc_split;
+  else while (((uint64_t)M << logT) < (1u << 18) && acc_entries / ((uint64_t)M << logT) > (uint64_t)(rounds > 0 ? 8 : ctx->opt_acc_min_entries)) logT++;
+  void* parts;
+  KZG_TRY(scratch_get(ctx, SCR_PARTIALS, ((size_t)M << logT) * sizeof(G1Xyzz), &parts));
+  {
+    auto kern = k_bucket_acc<3>;
+    if (ctx->opt_acc_minblocks == 4 || (ctx->opt_acc_minblocks == 0 && rounds > 0)) kern = k_bucket_acc<4>;
+    else if (ctx->opt_acc_minblocks == 5) kern = k_bucket_acc<5>;
+    else if (ctx->opt_acc_minblocks == 6) kern = k_bucket_acc<6>;
+    const uint32_t* perm = nullptr;
+    if (ctx->opt_acc_order) {
+      void* pm;
+      KZG_TRY(scratch_get(ctx, SCR_ORDER, (size_t)M * 4 + 16, &pm));
+      k_bucket_order<<<1, 1024, 0, ctx->stream>>>(acc_start, M, reinterpret_cast<uint32_t*>(pm));
+      KZG_LAUNCHED(ctx);
+      perm = reinterpret_cast<const uint32_t*>(pm);
+    }
+    if (rounds == 0) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
+    kern<<<blocks_for((uint64_t)M << logT, 128), 128, 0, ctx->stream>>>(
+        acc_start, acc_vals, acc_tab, acc_pitch, M, logT, heavy_cap, perm,
+        reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
+    KZG_LAUNCHED(ctx);
+    if (rounds == 0) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
+  }
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  {
+    void* hp;
+    KZG_TRY(scratch_get(ctx, SCR_HEAVY_PARTS, heavy_max * HEAVY_BLOCKS * sizeof(G1Xyzz), &hp));
+    k_bucket_heavy<<<dim3(HEAVY_BLOCKS, 16), 128, 0, ctx->stream>>>(
+        acc_start, acc_vals, acc_tab, acc_pitch, reinterpret_cast<G1Xyzz*>(hp), heavy_list, heavy_count);
+    KZG_LAUNCHED(ctx);
+    k_heavy_fold<<<8, 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(hp), logT, reinterpret_cast<G1Xyzz*>(parts),
+                                             heavy_list, heavy_count);
+    KZG_LAUNCHED(ctx);
+  }
+  KZG_TRY(reduce_buckets_multi(ctx, reinterpret_cast<G1Xyzz*>(parts), half, logT, B, results_dev));
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   return KZG_OK;
 }

@@ -107,7 +107,9 @@ __device__ __forceinline__ void warp_tree_sum(G1Xyzz& X, uint32_t lane) {
 // M/32 chains are resident at once: the tail is latency-bound.
 __global__ void __launch_bounds__(32)
 k_reduce_l1(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* __restrict__ W_out,
-            G1Xyzz* __restrict__ S_out) {
+            G1Xyzz* __restrict__ S_out, uint32_t pool_stride) {
+  // blockIdx.y = bucket set (reduce_buckets_multi): its partials follow the previous set's, its outputs live pool_stride on
+  parts += (size_t)blockIdx.y * M * T; W_out += (size_t)blockIdx.y * pool_stride; S_out += (size_t)blockIdx.y * pool_stride;
   const uint32_t lane = threadIdx.x;
   const uint32_t b = blockIdx.x * 32 + lane;
   G1Xyzz X; set_inf(X);
@@ -306,8 +308,9 @@ k_reduce_l1c(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* _
 // level 2, cooperative: block 2k runs the S chain of chunk k, block 2k+1 folds its W0 values
 __global__ void __launch_bounds__(128)
 k_reduce_l2c(const G1Xyzz* __restrict__ S0, const G1Xyzz* __restrict__ W0, uint32_t m,
-             G1Xyzz* __restrict__ S1, G1Xyzz* __restrict__ W1, G1Xyzz* __restrict__ V) {
+             G1Xyzz* __restrict__ S1, G1Xyzz* __restrict__ W1, G1Xyzz* __restrict__ V, uint32_t pool_stride) {
   __shared__ CoopBuf sh;
+  { const size_t o = (size_t)blockIdx.y * pool_stride; S0 += o; W0 += o; S1 += o; W1 += o; V += o; }
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t k = blockIdx.x >> 1;
   const uint32_t idx = k * 32 + lane;
@@ -329,8 +332,9 @@ k_reduce_l2c(const G1Xyzz* __restrict__ S0, const G1Xyzz* __restrict__ W0, uint3
 // level 3, cooperative, three blocks: 0: S1 -> (S_total, W2); 1: sum W1; 2: sum V.  res[0..3] = S_total, W2, sumW1, sumV
 __global__ void __launch_bounds__(128)
 k_reduce_l3c(const G1Xyzz* __restrict__ S1, const G1Xyzz* __restrict__ W1, const G1Xyzz* __restrict__ V, uint32_t m2,
-             G1Xyzz* __restrict__ res) {
+             G1Xyzz* __restrict__ res, uint32_t pool_stride) {
   __shared__ CoopBuf sh;
+  { const size_t o = (size_t)blockIdx.y * pool_stride; S1 += o; W1 += o; V += o; res += o; }
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const G1Xyzz* src = blockIdx.x == 0 ? S1 : (blockIdx.x == 1 ? W1 : V);
   G1Xyzz X;
@@ -349,8 +353,10 @@ k_reduce_l3c(const G1Xyzz* __restrict__ S1, const G1Xyzz* __restrict__ W1, const
 
 // Horner, cooperative: out = S_total + sumW0 + 32*(sumW1 + 32*(W2)), then the shallower pre-summed levels
 __global__ void __launch_bounds__(128)
-k_reduce_horner(const G1Xyzz* __restrict__ res, const G1Xyzz* __restrict__ pre, int npre, G1Xyzz* __restrict__ out) {
+k_reduce_horner(const G1Xyzz* __restrict__ res, const G1Xyzz* __restrict__ pre, int npre, G1Xyzz* __restrict__ out,
+                uint32_t pool_stride) {
   __shared__ CoopBuf sh;
+  res += (size_t)blockIdx.y * pool_stride; out += blockIdx.y;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   G1Xyzz acc = res[1];
 #pragma unroll 1
@@ -403,8 +409,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 __global__ void __launch_bounds__(128)
 k_exchange_combine(const G1Xyzz* __restrict__ mine, PeerTable peers, int world, int rank, uint32_t seq,
-                   long long timeout_cycles, uint8_t* __restrict__ out_c48, uint32_t* __restrict__ status) {
+                   long long timeout_cycles, uint8_t* __restrict__ out_c48, uint32_t* __restrict__ status, uint32_t out_stride) {
   __shared__ CoopBuf sh;
+  // block b = collective call number seq + b (calls fused into one bucket problem finish together: one launch for all)
+  mine += blockIdx.x; seq += blockIdx.x;
+  out_c48 += (size_t)blockIdx.x * out_stride;
+  status = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(status) + (size_t)blockIdx.x * out_stride);
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t par = seq & (KZG_P2P_DEPTH - 1);
   PeerMailbox* my = peers.box[rank];
@@ -454,12 +464,12 @@ k_exchange_combine(const G1Xyzz* __restrict__ mine, PeerTable peers, int world, 
 }
 
 int32_t exchange_combine(kzg_ctx* ctx, const kzg_ctx* owner, uint32_t seq, const G1Xyzz* mine_dev, uint8_t* out_c48_dev,
-                         uint32_t* status_dev) {
+                         uint32_t* status_dev, int calls, uint32_t out_stride) {
   if (owner->p2p_world < 1 || !owner->p2p_connected) return fail(ctx, KZG_E_BAD_ARG, "peer mailboxes not connected (kzg_p2p_init / kzg_p2p_connect)");
   PeerTable t;
   for (int r = 0; r < KZG_MAX_PEERS; r++) t.box[r] = r < owner->p2p_world ? reinterpret_cast<PeerMailbox*>(owner->p2p_box[r]) : nullptr;
-  k_exchange_combine<<<1, 128, 0, ctx->stream>>>(mine_dev, t, owner->p2p_world, owner->p2p_rank, seq, owner->p2p_timeout_cycles,
-                                                 out_c48_dev, status_dev);
+  k_exchange_combine<<<(unsigned)calls, 128, 0, ctx->stream>>>(mine_dev, t, owner->p2p_world, owner->p2p_rank, seq,
+                                                               owner->p2p_timeout_cycles, out_c48_dev, status_dev, out_stride);
   KZG_LAUNCHED(ctx);
   return KZG_OK;
 }
@@ -531,20 +541,47 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
     G1Xyzz* res = pool; pool += 4;
     // level 1 stays one warp per chunk: all M/32 chains are resident at once, which four warps per chunk are not
     if (ctx->opt_coop_tail == 2) k_reduce_l1c<<<m1, 128, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
-    else k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
+    else k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0, 0);
     KZG_LAUNCHED(ctx);
-    k_reduce_l2c<<<m2 * 2, 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V);
+    k_reduce_l2c<<<m2 * 2, 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V, 0);
     KZG_LAUNCHED(ctx);
-    k_reduce_l3c<<<3, 128, 0, ctx->stream>>>(S1, W1, V, m2, res);
+    k_reduce_l3c<<<3, 128, 0, ctx->stream>>>(S1, W1, V, m2, res, 0);
     KZG_LAUNCHED(ctx);
-    k_reduce_horner<<<1, 128, 0, ctx->stream>>>(res, pre, (int)shallow, result_dev);
+    k_reduce_horner<<<1, 128, 0, ctx->stream>>>(res, pre, (int)shallow, result_dev, 0);
     KZG_LAUNCHED(ctx);
     return KZG_OK;
   }
-  k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
+  k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0, 0);
   k_reduce_l2<<<blocks_for((uint64_t)m2 * 64, 128), 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V);
   KZG_LAUNCHED(ctx);
   k_reduce_l3<<<1, 96, 0, ctx->stream>>>(S1, W1, V, m2, pre, (int)shallow, result_dev);
+  KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
+// B bucket sets of M <= 32768 buckets each (msm_bucket_multi): the fused cooperative tail once, blockIdx.y = set
+int32_t reduce_buckets_multi(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, int B, G1Xyzz* results_dev) {
+  if (B == 1) return reduce_buckets(ctx, parts, M, logT, results_dev);
+  if (M > 32768) return fail(ctx, KZG_E_BAD_ARG, "fused bucket reduction: at most 32768 buckets per set");
+  const uint32_t m1 = (M + 31) / 32, m2 = (m1 + 31) / 32;
+  const uint32_t stride = 2 * m1 + 3 * m2 + 4;                 // S0 W0 | S1 W1 V | res, per set
+  void* ws;
+  KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, ((size_t)stride * (size_t)B + 16) * sizeof(G1Xyzz), &ws));
+  G1Xyzz* pool = reinterpret_cast<G1Xyzz*>(ws);
+  G1Xyzz* S0 = pool; pool += m1;
+  G1Xyzz* W0 = pool; pool += m1;
+  G1Xyzz* S1 = pool; pool += m2;
+  G1Xyzz* W1 = pool; pool += m2;
+  G1Xyzz* V = pool; pool += m2;
+  G1Xyzz* res = pool;
+  const unsigned nb = (unsigned)B;
+  k_reduce_l1<<<dim3(m1, nb), 32, 0, ctx->stream>>>(parts, M, 1u << logT, W0, S0, stride);
+  KZG_LAUNCHED(ctx);
+  k_reduce_l2c<<<dim3(m2 * 2, nb), 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V, stride);
+  KZG_LAUNCHED(ctx);
+  k_reduce_l3c<<<dim3(3, nb), 128, 0, ctx->stream>>>(S1, W1, V, m2, res, stride);
+  KZG_LAUNCHED(ctx);
+  k_reduce_horner<<<dim3(1, nb), 128, 0, ctx->stream>>>(res, nullptr, 0, results_dev, stride);
   KZG_LAUNCHED(ctx);
   return KZG_OK;
 }

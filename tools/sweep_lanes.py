@@ -15,14 +15,17 @@ lanes_list = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else 
 rest = sys.argv[3:]
 window = int(rest.pop(0)) if rest and "=" not in rest[0] else 0
 n = 1 << logn
-steps = 40 if logn >= 19 else 120
+steps = 48 if logn >= 19 else 144
 scal = util.scalar_stream_bytes(0xC3, n)
 exp = O.g1_compress(O.commit_known_secret(util.to_ints(scal), O.fr_from_be_bytes(O.BENCH_SECRET_BE)))
 for lanes in lanes_list:
     ctx = pkg.Context(0)
     ctx.set_option("lanes", lanes)
+    depth = lanes
     for kv in rest:
         k, v = kv.split("="); ctx.set_option(k, int(v))
+        if k == "msm_coalesce":
+            depth = lanes * int(v)                   # tickets that can be out at once
     st = ctx.setup_generate(synthetic.BENCH_SECRET_BE, n)
     st.prepare_msm(window)
     host = torch.from_numpy(synthetic.scalar_stream(0xC3, n)).pin_memory()
@@ -39,7 +42,7 @@ for lanes in lanes_list:
         import time
         q = deque()
         for _ in range(k):
-            if len(q) == lanes:
+            if len(q) == depth:
                 assert ctx.msm_g1_wait(q.popleft()) == ref
             t0 = time.perf_counter()
             q.append(submit())
@@ -50,7 +53,7 @@ for lanes in lanes_list:
     res = []
     for name, submit in (("dev", lambda: ctx.msm_g1_submit_dev(st, dev.data_ptr(), n)),
                          ("e2e", lambda: ctx.msm_g1_submit(st, host.data_ptr(), n))):
-        run(2 * lanes + 2, submit)
+        run(2 * depth + 2, submit)
         ctx.sync(); ctx.timer_start()
         host_s[0] = 0.0
         run(steps, submit)
