@@ -70,6 +70,7 @@ struct kzg_ctx {
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_tree_k = 0;                  // pairs per thread in the halving rounds: 0 = auto (fill the last wave), else 8..16
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
+  int opt_reduce_lk = -1;              // level 1 of the bucket reduction: log2 of the buckets a lane walks serially (msm_tail.cu k_reduce_l1k); -1 = auto
   int opt_acc_minblocks = 0;           // resident blocks per SM the accumulate kernel is compiled for (0 = auto: 4 after halving rounds, else 3)
   int sm_count = 148;
   // submission queue of kzg_msm_g1_submit / kzg_msm_g1_wait (host->device copy of call k+1 beside call k)

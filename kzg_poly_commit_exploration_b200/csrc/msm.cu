@@ -97,18 +97,53 @@ k_digit_count(ScalarPtrs sp, uint64_t n, int c, int W, uint32_t half, uint32_t* 
   }
 }
 
-// M <= 65536 counts, one block of 1024 threads: start[b] = sum of count[< b], start[M] = all entries; cursor = start
-__global__ void __launch_bounds__(1024)
-k_bucket_scan(const uint32_t* __restrict__ count, uint32_t M, uint32_t* __restrict__ start, uint32_t* __restrict__ cursor) {
+// start[b] = sum of count[< b], start[M] = all entries; cursor = start.  Two launches over tiles of 1024 counts (a single
+// block took 164 us of load latency at M = 65536, the buckets of four fused calls): per-tile totals, then every tile adds
+// up the totals in front of it and scans its own counts.
+constexpr int SCAN_TILE = 1024;
+__global__ void __launch_bounds__(SCAN_TILE)
+k_bucket_tile_totals(const uint32_t* __restrict__ count, uint32_t M, uint32_t* __restrict__ tile_tot) {
   __shared__ uint32_t warp_tot[32];
-  const uint32_t per = (M + 1023) / 1024;            // consecutive counts per thread
-  const uint32_t b0 = threadIdx.x * per;
-  uint32_t local = 0;
-  for (uint32_t k = 0; k < per; k++) if (b0 + k < M) local += __ldg(count + b0 + k);
+  const uint32_t b = blockIdx.x * SCAN_TILE + threadIdx.x;
+  uint32_t v = b < M ? __ldg(count + b) : 0u;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = warp_tot[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = v;
+  }
+}
+// ntiles <= 1024
+__global__ void __launch_bounds__(SCAN_TILE)
+k_bucket_scan(const uint32_t* __restrict__ count, uint32_t M, const uint32_t* __restrict__ tile_tot,
+              uint32_t* __restrict__ start, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t base_sh;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // totals of the tiles in front of this one
+  uint32_t v = threadIdx.x < blockIdx.x ? __ldg(tile_tot + threadIdx.x) : 0u;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  if (lane == 0) warp_tot[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = warp_tot[lane];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) base_sh = v;
+  }
+  __syncthreads();
+  const uint32_t base = base_sh;
+  const uint32_t b = blockIdx.x * SCAN_TILE + threadIdx.x;
+  const uint32_t local = b < M ? __ldg(count + b) : 0u;
   uint32_t inc = local;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += t; }
+  __syncthreads();
   if (lane == 31) warp_tot[w] = inc;
   __syncthreads();
   if (w == 0) {
@@ -118,11 +153,9 @@ k_bucket_scan(const uint32_t* __restrict__ count, uint32_t M, uint32_t* __restri
     warp_tot[lane] = xi - x;
   }
   __syncthreads();
-  uint32_t run = warp_tot[w] + inc - local;
-  for (uint32_t k = 0; k < per; k++) {
-    if (b0 + k < M) { start[b0 + k] = run; cursor[b0 + k] = run; run += __ldg(count + b0 + k); }
-  }
-  if (threadIdx.x == 1023) start[M] = run;           // the last thread's running sum is the grand total
+  const uint32_t ex = base + warp_tot[w] + inc - local;
+  if (b < M) { start[b] = ex; cursor[b] = ex; }
+  if (b == M - 1) start[M] = ex + local;
 }
 
 __global__ void __launch_bounds__(256)
@@ -292,6 +325,18 @@ int32_t set_infinity(kzg_ctx* ctx, G1Xyzz* out_dev, uint32_t count) {
   return KZG_OK;
 }
 
+// count[0..M) -> start[0..M], cursor[0..M); the tile totals live behind cursor (the arena is sized for them)
+static int32_t launch_bucket_scan(kzg_ctx* ctx, const uint32_t* count, uint32_t M, uint32_t* start, uint32_t* cursor) {
+  const uint32_t ntiles = (M + SCAN_TILE - 1) / SCAN_TILE;
+  if (ntiles > SCAN_TILE) return fail(ctx, KZG_E_BAD_ARG, "too many buckets for the counting sort");
+  uint32_t* tile_tot = cursor + M + 2;
+  k_bucket_tile_totals<<<ntiles, SCAN_TILE, 0, ctx->stream>>>(count, M, tile_tot);
+  KZG_LAUNCHED(ctx);
+  k_bucket_scan<<<ntiles, SCAN_TILE, 0, ctx->stream>>>(count, M, tile_tot, start, cursor);
+  KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
 // affine halving rounds by problem size (measured, profiles/sweep_tree_rounds_r01.txt, sweep_lanes_r01.txt): one per
 // doubling of the entry count from 2^20 entries on - 2 at n = 2^17, 5 at n = 2^20 (c = 16), at most 6.  A round's
 // inversion chain is ~0.15 ms of latency; with several calls in flight (lanes) that latency is covered by the bulk
@@ -331,15 +376,14 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   if (counting) {
     // counting sort: count -> scan -> scatter (see above); count[] and cursor[] share one small arena
     void* cc;
-    KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)half * 2 + 8) * 4, &cc));
+    KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)half * 2 + 8 + SCAN_TILE) * 4, &cc));
     uint32_t* count = reinterpret_cast<uint32_t*>(cc);
     uint32_t* cursor = count + half + 4;
     KZG_CUDA_OK(ctx, cudaMemsetAsync(count, 0, (size_t)half * 4, ctx->stream));
     ScalarPtrs sp = {}; sp.p[0] = scalars_dev;
     k_digit_count<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(sp, n, c, W, half, count);
     KZG_LAUNCHED(ctx);
-    k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(count, half, reinterpret_cast<uint32_t*>(st), cursor);
-    KZG_LAUNCHED(ctx);
+    KZG_TRY(launch_bucket_scan(ctx, count, half, reinterpret_cast<uint32_t*>(st), cursor));
     k_digit_scatter<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(sp, n, c, W, s->n, half, cursor, reinterpret_cast<uint32_t*>(vb));
     KZG_LAUNCHED(ctx);
   } else {
@@ -457,7 +501,7 @@ int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const*
   KZG_TRY(scratch_get(ctx, SCR_HEAVY, (heavy_max + 1) * 4, &hv));
   uint32_t* heavy_count = reinterpret_cast<uint32_t*>(hv);
   uint32_t* heavy_list = heavy_count + 1;
-  KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)M * 2 + 8) * 4, &cc));
+  KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)M * 2 + 8 + SCAN_TILE) * 4, &cc));
   uint32_t* count = reinterpret_cast<uint32_t*>(cc);
   uint32_t* cursor = count + M + 4;
 
@@ -467,8 +511,7 @@ int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const*
   KZG_CUDA_OK(ctx, cudaMemsetAsync(count, 0, (size_t)M * 4, ctx->stream));
   k_digit_count<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, half, count);
   KZG_LAUNCHED(ctx);
-  k_bucket_scan<<<1, 1024, 0, ctx->stream>>>(count, M, reinterpret_cast<uint32_t*>(st), cursor);
-  KZG_LAUNCHED(ctx);
+  KZG_TRY(launch_bucket_scan(ctx, count, M, reinterpret_cast<uint32_t*>(st), cursor));
   k_digit_scatter<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, s->n, half, cursor,
                                                                                  reinterpret_cast<uint32_t*>(vb));
   KZG_LAUNCHED(ctx);

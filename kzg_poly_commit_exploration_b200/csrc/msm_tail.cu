@@ -7,6 +7,7 @@
 // as a real function (KZG_FQ_NOINLINE: arguments in registers, one 6 KB copy), which keeps the whole tail
 // inside the instruction cache.
 #define KZG_FQ_NOINLINE 1
+#include <algorithm>
 #include "engine.cuh"
 
 namespace kzg {
@@ -123,6 +124,44 @@ k_reduce_l1(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* __
   if (lane == 0) set_inf(X);
   warp_tree_sum(X, lane);
   if (lane == 0) W_out[blockIdx.x] = X;
+}
+
+// level 1 for calls that run for THROUGHPUT (several in flight, or fused): with the machine shared between calls what
+// counts is the work, not the length of the chain.  k_reduce_l1 spends 10 warp-wide additions on every 32 buckets (the
+// suffix scan and the tree keep half the lanes idle); here a lane first walks 2^LK consecutive buckets with the
+// running-sum recurrence (acc += B_i; run += acc: two additions per bucket), and the warp-level steps are paid once per
+// 32 * 2^LK buckets: 2 + 15 / 2^LK additions per bucket instead of 10.
+//   lane: S_l = sum_i B_{b0+i}, W_l = sum_i i * B_{b0+i};  warp: S = sum_l S_l, W = 2^LK * sum_l l * S_l + sum_l W_l
+template <int LK>
+__global__ void __launch_bounds__(32)
+k_reduce_l1k(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* __restrict__ W_out,
+             G1Xyzz* __restrict__ S_out, uint32_t pool_stride) {
+  parts += (size_t)blockIdx.y * M * T; W_out += (size_t)blockIdx.y * pool_stride; S_out += (size_t)blockIdx.y * pool_stride;
+  constexpr uint32_t K = 1u << LK;
+  const uint32_t lane = threadIdx.x;
+  const uint32_t b0 = (blockIdx.x * 32 + lane) * K;
+  G1Xyzz acc, run; set_inf(acc); set_inf(run);
+#pragma unroll 1
+  for (int i = (int)K - 1; i >= 0; i--) {
+    const uint32_t b = b0 + (uint32_t)i;
+    if (b < M) {
+#pragma unroll 1
+      for (uint32_t k = 0; k < T; k++) { G1Xyzz o = parts[(size_t)b * T + k]; add(acc, o); }
+    }
+    if (i > 0) add(run, acc);
+  }
+  G1Xyzz Z = run;
+  warp_tree_sum(Z, lane);                     // sum_l W_l
+  warp_suffix_scan(acc, lane);                // R_l = sum_{m >= l} S_m
+  if (lane == 0) S_out[blockIdx.x] = acc;
+  if (lane == 0) set_inf(acc);
+  warp_tree_sum(acc, lane);                   // sum_{l >= 1} R_l = sum_l l * S_l
+  if (lane == 0) {
+#pragma unroll 1
+    for (int k = 0; k < LK; k++) dbl(acc);
+    add(acc, Z);
+    W_out[blockIdx.x] = acc;
+  }
 }
 
 // level 2: chunk k of 32 level-1 outputs.  Even warps run the S chain (-> S1_k, W1_k), odd warps fold the
@@ -354,15 +393,17 @@ k_reduce_l3c(const G1Xyzz* __restrict__ S1, const G1Xyzz* __restrict__ W1, const
 // Horner, cooperative: out = S_total + sumW0 + 32*(sumW1 + 32*(W2)), then the shallower pre-summed levels
 __global__ void __launch_bounds__(128)
 k_reduce_horner(const G1Xyzz* __restrict__ res, const G1Xyzz* __restrict__ pre, int npre, G1Xyzz* __restrict__ out,
-                uint32_t pool_stride) {
+                uint32_t pool_stride, int l1_shift) {
+  // l1_shift = log2 of the buckets per level-1 chunk (5, or 5 + LK after k_reduce_l1k): the weight of the step that adds sum W0
   __shared__ CoopBuf sh;
   res += (size_t)blockIdx.y * pool_stride; out += blockIdx.y;
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   G1Xyzz acc = res[1];
 #pragma unroll 1
   for (int l = 0; l < 2 + npre; l++) {
+    const int shift = l == 1 ? l1_shift : 5;
 #pragma unroll 1
-    for (int k = 0; k < 5; k++) dbl4(acc, &sh, w, lane);
+    for (int k = 0; k < shift; k++) dbl4(acc, &sh, w, lane);
     G1Xyzz t = l == 0 ? res[2] : (l == 1 ? res[3] : pre[npre - 1 - (l - 2)]);
     add4(acc, t, true, &sh, w, lane);
   }
@@ -499,6 +540,20 @@ int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* o
   return KZG_OK;
 }
 
+// buckets a lane of level 1 walks serially (log2): 0 = k_reduce_l1 (shortest chain, a call on its own), else k_reduce_l1k
+static int l1_chunk_log(const kzg_ctx* ctx, uint32_t M) {
+  if (ctx->opt_reduce_lk >= 0) return std::min(3, ctx->opt_reduce_lk);
+  if (!ctx->throughput_mode) return 0;
+  return M >= 8192 ? 2 : (M >= 2048 ? 1 : 0);
+}
+static void launch_l1(kzg_ctx* ctx, int lk, dim3 grid, const G1Xyzz* parts, uint32_t M, uint32_t T, G1Xyzz* W0, G1Xyzz* S0,
+                      uint32_t stride) {
+  if (lk == 1) k_reduce_l1k<1><<<grid, 32, 0, ctx->stream>>>(parts, M, T, W0, S0, stride);
+  else if (lk == 2) k_reduce_l1k<2><<<grid, 32, 0, ctx->stream>>>(parts, M, T, W0, S0, stride);
+  else if (lk == 3) k_reduce_l1k<3><<<grid, 32, 0, ctx->stream>>>(parts, M, T, W0, S0, stride);
+  else k_reduce_l1<<<grid, 32, 0, ctx->stream>>>(parts, M, T, W0, S0, stride);
+}
+
 // sum_b (b+1) * A_b -> result_dev, where A_b = sum_k parts[b*T + k], T = 2^logT partials per bucket
 int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, G1Xyzz* result_dev) {
   // shallow levels (only for M > 32768, i.e. windows wider than 16 bits) run one launch per step and leave
@@ -531,7 +586,8 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
       cur = S; m = k;
     }
   }
-  const uint32_t m1 = (m + 31) / 32, m2 = (m1 + 31) / 32;
+  const int lk = (shallow == 0 && ctx->opt_coop_tail == 1) ? l1_chunk_log(ctx, m) : 0;
+  const uint32_t m1 = (m + (32u << lk) - 1) / (32u << lk), m2 = (m1 + 31) / 32;
   G1Xyzz* S0 = pool; pool += m1;
   G1Xyzz* W0 = pool; pool += m1;
   G1Xyzz* S1 = pool; pool += m2;
@@ -541,13 +597,13 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
     G1Xyzz* res = pool; pool += 4;
     // level 1 stays one warp per chunk: all M/32 chains are resident at once, which four warps per chunk are not
     if (ctx->opt_coop_tail == 2) k_reduce_l1c<<<m1, 128, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0);
-    else k_reduce_l1<<<m1, 32, 0, ctx->stream>>>(cur, m, 1u << logT, W0, S0, 0);
+    else launch_l1(ctx, lk, dim3(m1, 1), cur, m, 1u << logT, W0, S0, 0);
     KZG_LAUNCHED(ctx);
     k_reduce_l2c<<<m2 * 2, 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V, 0);
     KZG_LAUNCHED(ctx);
     k_reduce_l3c<<<3, 128, 0, ctx->stream>>>(S1, W1, V, m2, res, 0);
     KZG_LAUNCHED(ctx);
-    k_reduce_horner<<<1, 128, 0, ctx->stream>>>(res, pre, (int)shallow, result_dev, 0);
+    k_reduce_horner<<<1, 128, 0, ctx->stream>>>(res, pre, (int)shallow, result_dev, 0, 5 + lk);
     KZG_LAUNCHED(ctx);
     return KZG_OK;
   }
@@ -563,7 +619,8 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
 int32_t reduce_buckets_multi(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, int B, G1Xyzz* results_dev) {
   if (B == 1) return reduce_buckets(ctx, parts, M, logT, results_dev);
   if (M > 32768) return fail(ctx, KZG_E_BAD_ARG, "fused bucket reduction: at most 32768 buckets per set");
-  const uint32_t m1 = (M + 31) / 32, m2 = (m1 + 31) / 32;
+  const int lk = l1_chunk_log(ctx, M);
+  const uint32_t m1 = (M + (32u << lk) - 1) / (32u << lk), m2 = (m1 + 31) / 32;
   const uint32_t stride = 2 * m1 + 3 * m2 + 4;                 // S0 W0 | S1 W1 V | res, per set
   void* ws;
   KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, ((size_t)stride * (size_t)B + 16) * sizeof(G1Xyzz), &ws));
@@ -575,13 +632,13 @@ int32_t reduce_buckets_multi(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint
   G1Xyzz* V = pool; pool += m2;
   G1Xyzz* res = pool;
   const unsigned nb = (unsigned)B;
-  k_reduce_l1<<<dim3(m1, nb), 32, 0, ctx->stream>>>(parts, M, 1u << logT, W0, S0, stride);
+  launch_l1(ctx, lk, dim3(m1, nb), parts, M, 1u << logT, W0, S0, stride);
   KZG_LAUNCHED(ctx);
   k_reduce_l2c<<<dim3(m2 * 2, nb), 128, 0, ctx->stream>>>(S0, W0, m1, S1, W1, V, stride);
   KZG_LAUNCHED(ctx);
   k_reduce_l3c<<<dim3(3, nb), 128, 0, ctx->stream>>>(S1, W1, V, m2, res, stride);
   KZG_LAUNCHED(ctx);
-  k_reduce_horner<<<dim3(1, nb), 128, 0, ctx->stream>>>(res, nullptr, 0, results_dev, stride);
+  k_reduce_horner<<<dim3(1, nb), 128, 0, ctx->stream>>>(res, nullptr, 0, results_dev, stride, 5 + lk);
   KZG_LAUNCHED(ctx);
   return KZG_OK;
 }
