@@ -338,12 +338,13 @@ def msm_headline(args, R, pkg, synthetic, ctx, devices):
         return ctx.msm_g1_wait(t)
 
     r_ref = [None]
+    depth = args.lanes * args.coalesce       # tickets out at once: `lanes` groups of `coalesce` fused calls
 
     def calls_in_flight(k, submit):
         from collections import deque
         q, out = deque(), None
         for _ in range(k):
-            if len(q) == args.lanes:
+            if len(q) == depth:
                 out = ctx.msm_g1_wait(q.popleft())
                 assert out == r_ref[0], "a pipelined step returned a different commitment"
             q.append(submit())
@@ -391,7 +392,7 @@ def msm_headline(args, R, pkg, synthetic, ctx, devices):
     for _ in range(args.warmup):
         r_dev = step_dev()
     r_ref[0] = r_dev
-    steps_dev_pipelined(max(2 * args.lanes, args.warmup))
+    steps_dev_pipelined(max(2 * depth, args.warmup))
 
     stop, samples = threading.Event(), []
     th = threading.Thread(target=_clock_sampler, args=(stop, samples, R.local), daemon=True)
@@ -412,7 +413,7 @@ def msm_headline(args, R, pkg, synthetic, ctx, devices):
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     ms_e2e_sync, _, r_e2e = timed(loop(step_e2e), args.steps)
-    steps_e2e_pipelined(2 * args.lanes)
+    steps_e2e_pipelined(2 * depth)
     ms_e2e, _, r_pipe = timed(steps_e2e_pipelined, args.steps)
     assert r_pipe == r_e2e, "pipelined and synchronous host-buffer results differ"
     nccl = None
@@ -465,13 +466,16 @@ def msm_headline(args, R, pkg, synthetic, ctx, devices):
                    "sharding": f"point range, {per_dev} points/GPU",
                    "exchange": ("none" if n_gpus == 1 else "peer stores over NVLink + fold + compress in one kernel (k_exchange_combine)"),
                    "l2": f"inputs larger than L2 (table {plan['W'] * per_dev * plan['table_pitch'] / 2**20:.0f} MiB + scalars {per_dev * 32 / 2**20:.0f} MiB per GPU)",
-                   "precomputed_table_s": round(table_s, 3), "calls_in_flight": args.lanes,
-                   "step": f"one complete MSM (48-byte result read back and compared with the golden commitment); steps are submitted {args.lanes} deep "
-                           "(kzg_msm_g1_submit_dev / _wait), so the bulk kernels of one step overlap the latency-bound phases of the others"},
+                   "precomputed_table_s": round(table_s, 3), "calls_in_flight": depth, "lanes": args.lanes,
+                   "fused_calls": args.coalesce,
+                   "step": f"one complete MSM (48-byte result read back and compared with the golden commitment); steps are submitted {depth} deep "
+                           f"(kzg_msm_g1_submit_dev / _wait): {args.lanes} lanes, each running {args.coalesce} consecutive calls as ONE bucket problem "
+                           "(option msm_coalesce: bucket = call x 2^(c-1) + digit, same table), so the bulk kernels of one group overlap the "
+                           "latency-bound phases of the others"},
         "one_call_at_a_time": {"value": n_total / (single_step * 1e-3), "unit": "points/s", "ms_per_step": single_step},
         "e2e": {"value": n_total / (ms_e2e / args.steps * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n_total * 32,
                 "d2h_bytes_per_step": 48 * world, "ms_per_step": ms_e2e / args.steps,
-                "call": (f"kzg_msm_g1_submit / kzg_msm_g1_wait, {args.lanes} calls in flight, pinned host scalars"
+                "call": (f"kzg_msm_g1_submit / kzg_msm_g1_wait, {depth} calls in flight ({args.lanes} lanes x {args.coalesce} fused), pinned host scalars"
                          + ("" if world == 1 else " (kzg_msm_g1_sharded_submit: each rank copies its shard)")),
                 "one_call_at_a_time": {"value": n_total / (ms_e2e_sync / args.steps * 1e-3), "unit": "points/s",
                                        "ms_per_step": ms_e2e_sync / args.steps}},
@@ -791,7 +795,9 @@ def single_process_probe(args, R, pkg, synthetic):
             devs = list(range(R.world))
             g = pkg.Context(devs)
             g.set_option("lanes", args.lanes)
+            g.set_option("msm_coalesce", args.coalesce)
             g.set_option("setup_layout", 1)
+            depth = args.lanes * args.coalesce
             n = 1 << LOG_N
             st = g.setup_generate(synthetic.BENCH_SECRET_BE, n)
             st.prepare_msm(args.window)
@@ -802,18 +808,18 @@ def single_process_probe(args, R, pkg, synthetic):
             def run(k, submit):
                 q, out = deque(), None
                 for _ in range(k):
-                    if len(q) == args.lanes:
+                    if len(q) == depth:
                         out = g.msm_g1_wait(q.popleft())
                     q.append(submit())
                 while q:
                     out = g.msm_g1_wait(q.popleft())
                 return out
 
-            steps = max(8, args.steps // 2)
+            steps = max(2 * depth, args.steps)
             out = {}
             for name, submit in (("value", lambda: g.msm_g1_submit_dev(st, sc.data_ptr(), n)),
                                  ("e2e", lambda: g.msm_g1_submit(st, host.data_ptr(), n))):
-                run(2 * args.lanes, submit)
+                run(2 * depth, submit)
                 g.sync(); g.timer_start()
                 t0 = time.perf_counter()
                 r = run(steps, submit)
@@ -847,6 +853,9 @@ def run_ours(args):
     devices = list(range(args.gpus)) if (args.single_process and args.gpus > 1) else [R.local]
     ctx = pkg.Context(devices if len(devices) > 1 else devices[0])
     ctx.set_option("lanes", args.lanes)
+    if args.coalesce <= 0:      # auto: shares below 2^19 points are single-wave kernels on their own — fuse four of them
+        args.coalesce = 2 if ((1 << LOG_N) // max(1, args.gpus)) >= (1 << 19) else 4
+    ctx.set_option("msm_coalesce", args.coalesce)
 
     line, pk = msm_headline(args, R, pkg, synthetic, ctx, devices)
     extra = other_configs(args, R, pkg, synthetic, ctx, devices)
@@ -881,6 +890,8 @@ def main():
     ap.add_argument("--window", type=int, default=int(os.environ.get("KZG_WINDOW", "0")))
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("KZG_LANES", "4")),
                     help="MSM calls in flight per GPU for the headline throughput (1..4)")
+    ap.add_argument("--coalesce", type=int, default=int(os.environ.get("KZG_COALESCE", "0")),
+                    help="consecutive submitted MSM calls run as ONE bucket problem (option msm_coalesce, 1..4; 0 = by share size)")
     ap.add_argument("--blobs", type=int, default=int(os.environ.get("KZG_BLOBS", "4096")),
                     help="size of the secondary blob batch (0 = skip)")
     ap.add_argument("--fixed-window", type=int, default=int(os.environ.get("KZG_FIXED_WINDOW", "0")),
