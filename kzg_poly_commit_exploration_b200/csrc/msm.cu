@@ -491,7 +491,7 @@ int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const*
   const uint64_t total = (uint64_t)W * n * (uint64_t)B;
   if ((uint64_t)W * s->n >= (1ull << 31) || total >= (1ull << 32))
     return fail(ctx, KZG_E_BAD_ARG, "msm too large for 31-bit table indices");
-  if (half > 32768) return fail(ctx, KZG_E_BAD_ARG, "fused calls need a window of at most 16 bits");
+  if (half > (1u << 18) || (uint64_t)M > (1ull << 20)) return fail(ctx, KZG_E_BAD_ARG, "fused calls: too many buckets (window too wide)");
 
   void *vb, *st, *hv, *cc;
   KZG_TRY(scratch_get(ctx, SCR_VALS_B, total * 4, &vb));

@@ -543,8 +543,8 @@ int32_t sum_points(kzg_ctx* ctx, const G1Xyzz* in_dev, uint64_t count, G1Xyzz* o
 // buckets a lane of level 1 walks serially (log2): 0 = k_reduce_l1 (shortest chain, a call on its own), else k_reduce_l1k
 static int l1_chunk_log(const kzg_ctx* ctx, uint32_t M) {
   if (ctx->opt_reduce_lk >= 0) return std::min(3, ctx->opt_reduce_lk);
-  if (!ctx->throughput_mode) return 0;
-  return M >= 8192 ? 2 : (M >= 2048 ? 1 : 0);
+  if (!ctx->throughput_mode) return M > 32768 ? 1 : 0;      // a call on its own: the shortest chain that still fits the fused tail
+  return M > 32768 ? 3 : (M >= 8192 ? 2 : (M >= 2048 ? 1 : 0));
 }
 static void launch_l1(kzg_ctx* ctx, int lk, dim3 grid, const G1Xyzz* parts, uint32_t M, uint32_t T, G1Xyzz* W0, G1Xyzz* S0,
                       uint32_t stride) {
@@ -560,7 +560,9 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
   // their W sums in pre[]; the last three levels are the fused tail.
   void* ws;
   uint32_t shallow = 0;
-  for (uint32_t m = M; m > 32768; m = (m + 31) / 32) shallow++;
+  // the fused tail takes up to 1024 level-1 chunks: 32768 buckets with 32-bucket chunks, more with k_reduce_l1k's wider ones
+  const uint32_t fused_max = ctx->opt_coop_tail == 1 ? (32768u << l1_chunk_log(ctx, M)) : 32768u;
+  for (uint32_t m = M; m > fused_max; m = (m + 31) / 32) shallow++;
   size_t cap = (size_t)(M + 31) / 32 * 2 * 2 + 4096 + 16;
   KZG_TRY(scratch_get(ctx, SCR_XYZZ_TMP, cap * sizeof(G1Xyzz), &ws));
   G1Xyzz* pool = reinterpret_cast<G1Xyzz*>(ws);
@@ -618,8 +620,8 @@ int32_t reduce_buckets(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t l
 // B bucket sets of M <= 32768 buckets each (msm_bucket_multi): the fused cooperative tail once, blockIdx.y = set
 int32_t reduce_buckets_multi(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint32_t logT, int B, G1Xyzz* results_dev) {
   if (B == 1) return reduce_buckets(ctx, parts, M, logT, results_dev);
-  if (M > 32768) return fail(ctx, KZG_E_BAD_ARG, "fused bucket reduction: at most 32768 buckets per set");
   const int lk = l1_chunk_log(ctx, M);
+  if (M > (32768u << lk)) return fail(ctx, KZG_E_BAD_ARG, "fused bucket reduction: too many buckets per set");
   const uint32_t m1 = (M + (32u << lk) - 1) / (32u << lk), m2 = (m1 + 31) / 32;
   const uint32_t stride = 2 * m1 + 3 * m2 + 4;                 // S0 W0 | S1 W1 V | res, per set
   void* ws;

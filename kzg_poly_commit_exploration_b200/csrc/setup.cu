@@ -320,6 +320,11 @@ int auto_msm_window(uint64_t n) {
   // With the scalars folded to 254 bits (fr_fold_half) c = 15 needs 17 windows and c = 17 only 15; measured with the
   // fold (profiles/sweep_lanes_r01.txt): at n = 2^20 c = 17 saves 1/16 of the additions but doubles the bucket
   // reduction and ends up level (5.48 vs 5.51 ms); at n = 2^17 c = 15 wins (1.07 vs 1.10 ms).
+  // Round 2: the running-sum level 1 of the bucket reduction (msm_tail.cu k_reduce_l1k) made buckets cheap for calls that
+  // run for throughput (5.75 instead of 10+ additions per bucket), and with it c = 17 (15 windows, 65536 buckets) wins
+  // at n = 2^20: 5.06 -> 4.77 ms per MSM with eight calls in flight, two fused (profiles/sweep_coalesce_r02.txt); c = 18
+  // leaves a 3-bit top window (n / 4 entries per bucket: the heavy path) and loses.
+  if (n >= (1ull << 20)) return 17;
   if (n >= (1ull << 18)) return 16;
   if (n >= (1ull << 17)) return 15;
   int best = 4; double best_cost = 1e300;

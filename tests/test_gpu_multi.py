@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_total, ret):
+def _worker(rank, world, port, n_total, coalesce, ret):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import torch
@@ -31,16 +31,18 @@ def _worker(rank, world, port, n_total, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)      # only carries the 64-byte IPC handles
     torch.cuda.set_device(rank)
     ctx = pkg.Context(rank)
+    ctx.set_option("msm_coalesce", coalesce)      # > 1: consecutive collective calls run as one bucket problem, one exchange launch
+    depth = 4 * coalesce
     parallel.connect_peers(ctx, world, rank)
     first, count = parallel.shard_range(n_total, world, rank)
     setup = ctx.setup_generate(synthetic.BENCH_SECRET_BE, count, first=first)
     scal = torch.from_numpy(synthetic.scalar_stream(0xC3, count, start=first)).to(torch.device(f"cuda:{rank}"))
     outs = [ctx.msm_g1_sharded_dev(setup, scal.data_ptr(), count) for _ in range(5)]   # every mailbox slot, back to back
-    # four collective calls in flight (one per lane of the context), 19 calls: the 8-deep mailboxes wrap twice
+    # `depth` collective calls in flight (four lanes x fused calls), 19 + 2 * depth calls: the mailboxes (2 x 16 deep) wrap
     from collections import deque
     q = deque()
-    for _ in range(19):
-        if len(q) == 4:
+    for _ in range(19 + 2 * depth):
+        if len(q) == depth:
             outs.append(ctx.msm_g1_wait(q.popleft()))
         q.append(ctx.msm_g1_sharded_submit_dev(setup, scal.data_ptr(), count))
     while q:
@@ -48,7 +50,7 @@ def _worker(rank, world, port, n_total, ret):
     # the same from pinned host buffers (copy on the lane's copy stream)
     host = torch.from_numpy(synthetic.scalar_stream(0xC3, count, start=first)).pin_memory()
     for _ in range(6):
-        if len(q) == 4:
+        if len(q) == depth:
             outs.append(ctx.msm_g1_wait(q.popleft()))
         q.append(ctx.msm_g1_sharded_submit(setup, host.data_ptr(), count))
     while q:
@@ -59,7 +61,8 @@ def _worker(rank, world, port, n_total, ret):
     dist.destroy_process_group()
 
 
-def test_two_gpu_peer_exchange_matches_single_gpu():
+@pytest.mark.parametrize("coalesce", [1, 4])
+def test_two_gpu_peer_exchange_matches_single_gpu(coalesce):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -74,7 +77,7 @@ def test_two_gpu_peer_exchange_matches_single_gpu():
     mpc = mp.get_context("spawn")
     ret = mpc.Queue()
     port = _free_port()
-    procs = [mpc.Process(target=_worker, args=(r, world, port, n_total, ret)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, port, n_total, coalesce, ret)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(ret.get(timeout=300) for _ in range(world))
@@ -84,4 +87,4 @@ def test_two_gpu_peer_exchange_matches_single_gpu():
     ints = [int.from_bytes(full[i].tobytes(), "little") for i in range(n_total)]
     expect = O.g1_compress(O.commit_known_secret(ints, O.fr_from_be_bytes(synthetic.BENCH_SECRET_BE))).hex()
     for r in range(world):
-        assert len(got[r]) == 5 + 19 + 6 and got[r] == [expect] * len(got[r]), r
+        assert len(got[r]) == 5 + 19 + 8 * coalesce + 6 and got[r] == [expect] * len(got[r]), r

@@ -633,9 +633,10 @@ def test_config_c3_msm_2_20(ctx):
     expect = O.g1_compress(O.commit_known_secret(ints, S))
     got = ctx.msm_g1(st, scal)
     assert got == expect
-    # the geometry bench.py reports (kzg_msm_plan): 16-bit windows, 16 of them (255-bit folded scalars), 5 halving rounds
-    assert st.msm_plan(n) == {"c": 16, "W": 16, "buckets": 32768, "rounds": 5, "table_pitch": 128}
-    assert st.msm_plan(1 << 17)["rounds"] == 2
+    # the geometry bench.py reports (kzg_msm_plan): 17-bit windows, 15 of them (255-bit folded scalars), 4 halving rounds
+    # for a call on its own (auto_tree_rounds: 15 x 2^20 entries; fused calls count their entries together: 5)
+    assert st.msm_plan(n) == {"c": 17, "W": 15, "buckets": 65536, "rounds": 4, "table_pitch": 128}
+    assert st.msm_plan(1 << 17)["rounds"] == 1
     # same result without the halving rounds and without the cooperative tail (independent code paths)
     for name, val in (("msm_tree_rounds", 0), ("coop_tail", 0)):
         ctx.set_option(name, val)
