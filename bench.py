@@ -853,8 +853,8 @@ def run_ours(args):
     devices = list(range(args.gpus)) if (args.single_process and args.gpus > 1) else [R.local]
     ctx = pkg.Context(devices if len(devices) > 1 else devices[0])
     ctx.set_option("lanes", args.lanes)
-    if args.coalesce <= 0:      # auto: shares below 2^19 points are single-wave kernels on their own — fuse four of them
-        args.coalesce = 2 if ((1 << LOG_N) // max(1, args.gpus)) >= (1 << 19) else 4
+    if args.coalesce <= 0:      # auto: the smaller the share, the more a call's kernels are single partial waves — fuse four of them
+        args.coalesce = 2 if ((1 << LOG_N) // max(1, args.gpus)) >= (1 << 20) else 4
     ctx.set_option("msm_coalesce", args.coalesce)
 
     line, pk = msm_headline(args, R, pkg, synthetic, ctx, devices)

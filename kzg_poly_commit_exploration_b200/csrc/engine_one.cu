@@ -577,7 +577,11 @@ static int32_t flush_open_group(kzg_ctx* ctx) {
     KZG_TRY(scratch_get(lane, SCR_OUT, 64 * KZG_MAX_COALESCE, &o));  // per call 48 compressed bytes (+ the status word of an exchange)
     G1Xyzz* res = reinterpret_cast<G1Xyzz*>(r);
     uint8_t* out_dev = reinterpret_cast<uint8_t*>(o);
-    lane->throughput_mode = ctx->lanes_in_use > 1 || B > 1;   // several calls in flight: tuned for throughput, not for the shortest chain
+    // tuned for throughput instead of the shortest chain when calls ARE in flight together: a fused group, or tickets of
+    // earlier groups that nobody has collected yet (a caller that submits and waits one call at a time keeps the short chain)
+    int others = 0;
+    for (uint32_t k = 0; k < slots; k++) others += (ctx->pending[k].busy && ctx->pending[k].launched) ? 1 : 0;
+    lane->throughput_mode = B > 1 || others > 0;
     int32_t st = KZG_OK;
     if (B == 1 || n == 0 || (s->fix_tab && n <= s->fix_n)) {
       for (int k = 0; k < B && st == KZG_OK; k++) st = msm_any(lane, s, q[k]->dev_scalars, n, res + k);

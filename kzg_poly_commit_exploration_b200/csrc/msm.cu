@@ -369,10 +369,10 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   uint32_t* heavy_list = heavy_count + 1;
 
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-  // measured (profiles/sweep_sort_r02.txt): the atomics of the counting sort cost 0.47 ms at 16.8 M entries against 0.37 ms
-  // for recode + radix sort + bounds, but its three launches win below ~2^22 entries (n = 2^17, four lanes: 1.027 -> 1.002 ms;
-  // n = 2^14: 0.354 -> 0.336 ms)
-  const bool counting = ctx->opt_msm_sort == 0 || (ctx->opt_msm_sort < 0 && total <= (1ull << 22));
+  // Counting sort at every size since the scan is tiled (two launches): 21 ps per entry at 31 M entries (two fused calls at
+  // n = 2^20, profiles/launches_r02_fused_n20.csv) against 22 ps for recode + two radix passes + bounds at 16-bit keys —
+  // and 17-bit keys (n >= 2^20) would cost the radix sort a third pass.  The cub path stays behind option msm_sort = 1.
+  const bool counting = ctx->opt_msm_sort <= 0;
   if (counting) {
     // counting sort: count -> scan -> scatter (see above); count[] and cursor[] share one small arena
     void* cc;
