@@ -8,7 +8,8 @@
 A "step" is one commit-MSM of n = 2^20 synthetic scalars U(0xC3, i) (BASELINE config C3) against the
 powers-of-tau setup of the reference's bench secret (00 01 .. 1f); every step's 48-byte commitment is read back and
 compared with the golden value (known-secret identity, tests/golden/bench_commitment.json).
-  value  : points/s, scalars resident in HBM, `lanes` calls in flight (kzg_msm_g1_submit_dev / _wait)
+  value  : points/s, scalars resident in HBM, `lanes` x `coalesce` calls in flight (kzg_msm_g1_submit_dev / _wait; option
+           msm_coalesce: consecutive calls run as ONE bucket problem), the one-call-at-a-time figure beside it
   e2e    : the same through the host-buffer C-ABI calls: pinned host scalars, 32 MiB H2D + 48 B D2H inside the timed region
   N > 1  : one process per GPU (torchrun); rank g owns bases / scalars [g n/N, (g+1) n/N) (point-range sharding); the
            192-byte partial sums are exchanged by ONE kernel over NVLink peer memory (k_exchange_combine), with an NCCL
@@ -42,7 +43,7 @@ CANONICAL_MAC_PER_POINT = 48000  # c = 16: 16 windows x 3000 (SURVEY 8d canonica
 CANONICAL_MAC_PER_BLOB = 8191 * CANONICAL_MAC_PER_POINT   # commit (4096 points) + proof (4095): 3.93e8
 NOMINAL_LANES_PER_CLK_SM = 64    # 32-bit integer multiply lanes per clock and SM (SURVEY 8d's assumption)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/*_summary.txt)
-TRAFFIC_NCU = {"k_seg_add<true>": 2.707788288e9 + 0.814427904e9,        # n = 2^20, c = 16 (profiles/prof_seg_add_r01j_summary.txt)
+TRAFFIC_NCU = {"k_seg_add<true>": 2.513057e9 + 0.738046720e9,          # n = 2^20, c = 17 (profiles/prof_seg_add_lean_r1_r02_summary.txt)
                "k_r1_add": 32.104460e9 + 8.170288e9}                     # 2048 rows x 4096, c = 15 (profiles/prof_r1_add_r02_summary.txt)
 GOLDEN_C3_COMMITMENT = "a9a29f4f21d2c6481dc286c676d58f57b1796df6e04854503c6d5348c202851fd361a5ec4624bee2e1a27092e80f7241"
 DTYPE = "u32-limb modular integer (Fq 381-bit, Fr 255-bit)"
@@ -450,7 +451,7 @@ def msm_headline(args, R, pkg, synthetic, ctx, devices):
     rounds = plan["rounds"]
     tree = rounds > 0
     dom_adds = adds // 2 if tree else adds          # round 1 pairs up all entries: half of the additions
-    dom_name = "k_seg_add<true> (round-1 pair additions of the affine halving, msm_tree.cu)" if tree else "k_bucket_acc"
+    dom_name = "k_seg_add_lean<true, 4> (round-1 pair additions of the affine halving, msm_tree.cu)" if tree else "k_bucket_acc"
     phase_achieved = adds * MAC_PER_BUCKET_ADD / (acc * 1e-3)
     dom_impl = dom_adds * (1500 if tree else 3000) / (dom * 1e-3)
     hbm_bytes = dom_adds * (2 * 96 + 2 * 4 + 48 + 96) if tree else adds * 100  # per pair: two table points, two indices, prefix in, point out
@@ -509,15 +510,16 @@ def msm_headline(args, R, pkg, synthetic, ctx, devices):
             "fq_mul_probe": {"per_s": pk["fq_mul_per_s"], "wide_mac_per_s": pk["fq_mul_per_s"] * MAC_PER_FQ_MUL,
                              "frac_of_measured_peak": pk["fq_mul_per_s"] * MAC_PER_FQ_MUL / pk["measured"],
                              "what": "the shipped carry-chained Montgomery product on all SMs: the practical ceiling of every kernel above"},
-            "int_pipe_busy_ncu": {"k_seg_add<true>": 0.734, "k_seg_add<false>": 0.804,
+            "int_pipe_busy_ncu": {"k_seg_add_lean<true, 4>": 0.757, "k_seg_add_lean<false, 4>": 0.821,
                                   "metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed (the pipe that "
                                             "executes IMAD / IMAD.WIDE), ncu --set full captures summarised in "
-                                            "profiles/prof_seg_add_r01j_summary.txt and prof_seg_add_dense_r01_summary.txt"},
+                                            "profiles/prof_seg_add_lean_r1_r02_summary.txt and prof_seg_add_lean_dense_r02_summary.txt"},
             "canonical_frac": canonical / pk["measured"], "canonical_frac_nominal": canonical / pk["nominal"],
             "canonical_note": "48 000 wide-MAC per point (SURVEY 8d) x points per device / pipelined step",
-            "traffic": TRAFFIC_NCU["k_seg_add<true>"] if tree and per_dev == (1 << 20) else None,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add<true> launch at n = 2^20 per device "
-                            "(the dominant kernel), profiles/prof_seg_add_r01j_summary.txt"},
+            "traffic": TRAFFIC_NCU["k_seg_add<true>"] if tree and per_dev == (1 << 20) and plan["c"] == 17 else None,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_seg_add_lean<true, 4> launch at n = 2^20, c = 17 per device "
+                            "(the dominant kernel; 1.20 x its algorithmic bytes: the pad of the 128-byte table pitch), "
+                            "profiles/prof_seg_add_lean_r1_r02_summary.txt"},
     }
     if nccl:
         line["exchange_nccl"] = nccl

@@ -168,13 +168,23 @@ k_digit_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint
   Fr k; ld_scalar(k, scalars + i * 32);
   fr_canon_reduce(k);
   SignedDigits sd; sd.init(k, c);
+  // four digits at a time: their atomics are in flight together (the returned slot is only needed for the store)
 #pragma unroll 1
-  for (int j = 0; j < W; j++) {
-    bool neg;
-    const uint32_t d = sd.next(j, &neg);
-    if (!d) continue;
-    const uint32_t slot = atomicAdd(cursor + (d - 1), 1u);
-    vals[slot] = (uint32_t)((uint64_t)j * n_stride + i) | (neg ? 0x80000000u : 0u);
+  for (int j0 = 0; j0 < W; j0 += 4) {
+    uint32_t dd[4], vv[4], slot[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      dd[u] = 0; vv[u] = 0;
+      if (j0 + u < W) {
+        bool neg;
+        dd[u] = sd.next(j0 + u, &neg);
+        vv[u] = (uint32_t)((uint64_t)(j0 + u) * n_stride + i) | (neg ? 0x80000000u : 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (dd[u]) slot[u] = atomicAdd(cursor + (dd[u] - 1), 1u);
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (dd[u]) vals[slot[u]] = vv[u];
   }
 }
 

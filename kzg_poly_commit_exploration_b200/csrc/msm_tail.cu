@@ -130,7 +130,7 @@ k_reduce_l1(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* __
 // counts is the work, not the length of the chain.  k_reduce_l1 spends 10 warp-wide additions on every 32 buckets (the
 // suffix scan and the tree keep half the lanes idle); here a lane first walks 2^LK consecutive buckets with the
 // running-sum recurrence (acc += B_i; run += acc: two additions per bucket), and the warp-level steps are paid once per
-// 32 * 2^LK buckets: 2 + 15 / 2^LK additions per bucket instead of 10.
+// 32 * 2^LK buckets: 2 + 11 / 2^LK additions (+ LK doublings per lane) per bucket instead of 10.
 //   lane: S_l = sum_i B_{b0+i}, W_l = sum_i i * B_{b0+i};  warp: S = sum_l S_l, W = 2^LK * sum_l l * S_l + sum_l W_l
 template <int LK>
 __global__ void __launch_bounds__(32)
@@ -150,18 +150,15 @@ k_reduce_l1k(const G1Xyzz* __restrict__ parts, uint32_t M, uint32_t T, G1Xyzz* _
     }
     if (i > 0) add(run, acc);
   }
-  G1Xyzz Z = run;
-  warp_tree_sum(Z, lane);                     // sum_l W_l
   warp_suffix_scan(acc, lane);                // R_l = sum_{m >= l} S_m
   if (lane == 0) S_out[blockIdx.x] = acc;
+  // sum_l (2^LK * l * S_l + W_l) = sum_l Y_l with Y_l = 2^LK * R_l (l >= 1) + W_l: ONE tree instead of two
   if (lane == 0) set_inf(acc);
-  warp_tree_sum(acc, lane);                   // sum_{l >= 1} R_l = sum_l l * S_l
-  if (lane == 0) {
 #pragma unroll 1
-    for (int k = 0; k < LK; k++) dbl(acc);
-    add(acc, Z);
-    W_out[blockIdx.x] = acc;
-  }
+  for (int k = 0; k < LK; k++) dbl(acc);
+  add(acc, run);
+  warp_tree_sum(acc, lane);
+  if (lane == 0) W_out[blockIdx.x] = acc;
 }
 
 // level 2: chunk k of 32 level-1 outputs.  Even warps run the S chain (-> S1_k, W1_k), odd warps fold the
