@@ -44,7 +44,7 @@ CANONICAL_MAC_PER_BLOB = 8191 * CANONICAL_MAC_PER_POINT   # commit (4096 points)
 NOMINAL_LANES_PER_CLK_SM = 64    # 32-bit integer multiply lanes per clock and SM (SURVEY 8d's assumption)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/*_summary.txt)
 TRAFFIC_NCU = {"k_seg_add<true>": 2.513057e9 + 0.738046720e9,          # n = 2^20, c = 17 (profiles/prof_seg_add_lean_r1_r02_summary.txt)
-               "k_r1_add": 32.104460e9 + 8.170288e9}                     # 2048 rows x 4096, c = 15 (profiles/prof_r1_add_r02_summary.txt)
+               "k_r1_add": 28.939577e9 + 8.170940e9}                     # 2048 rows x 4096, c = 15, row-minor mapping (profiles/prof_r1_add_r02n_summary.txt)
 GOLDEN_C3_COMMITMENT = "a9a29f4f21d2c6481dc286c676d58f57b1796df6e04854503c6d5348c202851fd361a5ec4624bee2e1a27092e80f7241"
 DTYPE = "u32-limb modular integer (Fq 381-bit, Fr 255-bit)"
 CRITERION_DEGREES = (1, 100, 500, 1000, 2500)     # benches/polynomial_commitment.rs:26-32
@@ -733,7 +733,7 @@ def blob_batch(args, R, pkg, synthetic, ctx, devices, pk):
                               "what": f"all rounds of the {rows}-row commit batch: {adds_all} additions x 3000 wide-MAC"},
                "traffic": TRAFFIC_NCU["k_r1_add"] if (rows == 2048 and fplan["c"] == 15) else None,
                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_r1_add launch (2048 rows, c = 15): "
-                               "profiles/prof_r1_add_r02_summary.txt; 1.74 x the algorithmic bytes (96-byte table pitch)"}
+                               "profiles/prof_r1_add_r02n_summary.txt; 1.6 x the algorithmic bytes (96-byte table pitch)"}
     # the 13-bit table beside the default (memory / throughput trade on record), 1 GPU only
     alt = None
     if world == 1 and not group and args.alt_window and args.alt_window != fplan["c"]:

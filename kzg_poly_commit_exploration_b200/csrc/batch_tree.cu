@@ -49,11 +49,13 @@ __device__ __forceinline__ const G1Affine* tab_entry(const G1Affine* fix, uint64
 
 __global__ void __launch_bounds__(TR_THREADS)
 k_r1_den(const uint8_t* __restrict__ scalars, uint64_t rows, uint64_t n, uint64_t stride, const G1Affine* __restrict__ fix,
-         int c, int W, Fq* __restrict__ prefix, Fq* __restrict__ tot) {
+         int c, int W, Fq* __restrict__ prefix, Fq* __restrict__ tot, int row_minor) {
   const uint64_t T = rows * n;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const uint64_t row = t / n, i = t % n;
+  // row_minor: neighbouring threads hold the SAME coefficient index of neighbouring rows, so a warp's lookups fall into
+  // the two 2^(c-1)-entry sub-tables of one (coefficient, window pair) instead of 32 coefficients' worth of table
+  const uint64_t row = row_minor ? t % rows : t / n, i = row_minor ? t / rows : t % n;
   uint32_t dig[32];
   digits_of(scalars, row, i, stride, c, W, dig);
   const int KP = (W + 1) / 2;
@@ -71,11 +73,11 @@ k_r1_den(const uint8_t* __restrict__ scalars, uint64_t rows, uint64_t n, uint64_
 
 __global__ void __launch_bounds__(TR_THREADS)
 k_r1_add(const uint8_t* __restrict__ scalars, uint64_t rows, uint64_t n, uint64_t stride, const G1Affine* __restrict__ fix,
-         int c, int W, const Fq* __restrict__ prefix, const Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
+         int c, int W, const Fq* __restrict__ prefix, const Fq* __restrict__ tot_inv, G1Affine* __restrict__ out, int row_minor) {
   const uint64_t T = rows * n;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const uint64_t row = t / n, i = t % n;
+  const uint64_t row = row_minor ? t % rows : t / n, i = row_minor ? t / rows : t % n;
   uint32_t dig[32];
   digits_of(scalars, row, i, stride, c, W, dig);
   const int KP = (W + 1) / 2;
@@ -94,7 +96,7 @@ k_r1_add(const uint8_t* __restrict__ scalars, uint64_t rows, uint64_t n, uint64_
     ld_point(a, p1, (d1 >> 31) != 0);
     ld_point(b, p2, (d2 >> 31) != 0);
     pair_add(o, a, b, dinv);
-    G1Affine* dst = out + (size_t)t * KP + m;
+    G1Affine* dst = out + (size_t)(row * n + i) * KP + m;      // rows stay contiguous for the generic rounds
     st_fq(&dst->x, o.x); st_fq(&dst->y, o.y);
   }
 }
@@ -313,13 +315,13 @@ int32_t msm_fixed_batch_tree(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* sc
     const uint8_t* sc = scalars_dev + r0 * stride_scalars * 32;
     // round 1
     const uint64_t T = rows * n;
-    k_r1_den<<<blocks_for(T, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, n, stride_scalars, s->fix_tab, c, W, prefix, tot);
+    k_r1_den<<<blocks_for(T, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, n, stride_scalars, s->fix_tab, c, W, prefix, tot, ctx->opt_r1_row_minor);
     KZG_LAUNCHED(ctx);
     KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
     G1Affine* cur = reinterpret_cast<G1Affine*>(A);
     G1Affine* nxt = reinterpret_cast<G1Affine*>(B);
     KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));      // the dominant kernel of a blob batch (kzg_ctx_last_kernel_ms(2))
-    k_r1_add<<<blocks_for(T, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, n, stride_scalars, s->fix_tab, c, W, prefix, tot, cur);
+    k_r1_add<<<blocks_for(T, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, n, stride_scalars, s->fix_tab, c, W, prefix, tot, cur, ctx->opt_r1_row_minor);
     KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
     KZG_LAUNCHED(ctx);
     uint64_t L = n * KP;
@@ -371,12 +373,12 @@ int32_t fixed_base_points_tree(kzg_ctx* ctx, const G1Affine* tab, int c, int W, 
   for (uint64_t r0 = 0; r0 < N; r0 += chunk) {
     const uint64_t rows = N - r0 < chunk ? N - r0 : chunk;
     const uint8_t* sc = scalars_dev + r0 * 32;
-    k_r1_den<<<blocks_for(rows, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, 1, 1, tab, c, W, prefix, tot);
+    k_r1_den<<<blocks_for(rows, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, 1, 1, tab, c, W, prefix, tot, 0);
     KZG_LAUNCHED(ctx);
     KZG_TRY(batch_invert_inplace(ctx, tot, rows, inv_ws, top));
     G1Affine* cur = reinterpret_cast<G1Affine*>(A);
     G1Affine* nxt = reinterpret_cast<G1Affine*>(B);
-    k_r1_add<<<blocks_for(rows, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, 1, 1, tab, c, W, prefix, tot, cur);
+    k_r1_add<<<blocks_for(rows, TR_THREADS), TR_THREADS, 0, ctx->stream>>>(sc, rows, 1, 1, tab, c, W, prefix, tot, cur, 0);
     KZG_LAUNCHED(ctx);
     uint64_t L = KP;
     while (L > 1) {

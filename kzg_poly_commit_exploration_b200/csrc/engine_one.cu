@@ -242,6 +242,7 @@ int32_t one_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "inv_top") ctx->opt_inv_top = std::max<int64_t>(8, value);
   else if (n == "msm_tree_rounds") ctx->opt_msm_tree_rounds = (int)value;
   else if (n == "tree_min_rows") ctx->opt_tree_min_rows = (int)value;
+  else if (n == "r1_row_minor") ctx->opt_r1_row_minor = (int)value;
   else if (n == "tree_chunk_rows") ctx->opt_tree_chunk_rows = (int)value;
   else if (n == "tree_min_pairs") ctx->opt_tree_min_pairs = value;
   else if (n == "setup_tree_min") ctx->opt_setup_tree_min = (int)value;
@@ -458,7 +459,7 @@ int32_t one_msm_g1(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_le32
 void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
   dst->opt_msm_window = src->opt_msm_window; dst->opt_fixed_window = src->opt_fixed_window;
   dst->opt_reduce_chunk = src->opt_reduce_chunk; dst->opt_msm_sort = src->opt_msm_sort; dst->opt_acc_order = src->opt_acc_order; dst->opt_tree_lean = src->opt_tree_lean; dst->opt_tree_lean_r1 = src->opt_tree_lean_r1; dst->opt_heavy_cap = src->opt_heavy_cap; dst->opt_acc_split = src->opt_acc_split;
-  dst->opt_tree_min_rows = src->opt_tree_min_rows; dst->opt_tree_chunk_rows = src->opt_tree_chunk_rows;
+  dst->opt_tree_min_rows = src->opt_tree_min_rows; dst->opt_r1_row_minor = src->opt_r1_row_minor; dst->opt_tree_chunk_rows = src->opt_tree_chunk_rows;
   dst->opt_tree_min_pairs = src->opt_tree_min_pairs; dst->opt_inv_top_fan = src->opt_inv_top_fan; dst->opt_inv_top = src->opt_inv_top;
   dst->opt_msm_tree_rounds = src->opt_msm_tree_rounds; dst->opt_acc_min_entries = src->opt_acc_min_entries;
   dst->opt_fixed_table_max_bytes = src->opt_fixed_table_max_bytes; dst->opt_setup_layout = src->opt_setup_layout;

@@ -25,5 +25,7 @@ for r in range(reps):
     ctx.sync(); t0 = time.perf_counter()
     ctx.commit_open_batch_dev(st, coeffs.data_ptr(), blobs, n, zs.data_ptr(), cm.data_ptr(), ys.data_ptr(), pr.data_ptr())
     ctx.sync(); dt = time.perf_counter() - t0
-    print(f"rep {r}: {dt*1e3:.2f} ms  {blobs / dt:.0f} blobs/s", flush=True)
+    import hashlib
+    h = hashlib.sha256(cm.cpu().numpy().tobytes() + pr.cpu().numpy().tobytes() + ys.cpu().numpy().tobytes()).hexdigest()[:16]
+    print(f"rep {r}: {dt*1e3:.2f} ms  {blobs / dt:.0f} blobs/s  r1_add {ctx.last_kernel_ms(2):.3f} ms  outputs {h}", flush=True)
 st.close(); ctx.close()
