@@ -7,7 +7,8 @@
 //                 Windows are FOLDED: the setup holds 2^(c j) * P_i for every j (built once per
 //                 setup, setup.cu), so all W windows share one set of 2^(c-1) buckets and the
 //                 per-window reduction + c doublings per window disappear.
-//   2. sort     : radix sort of the (bucket, index) pairs (cub::DeviceRadixSort, c key bits).
+//   2. sort     : counting sort of the (bucket, index) entries (count / tiled scan / scatter; cub::DeviceRadixSort behind
+//                 option msm_sort = 1).
 //   3. bounds   : bucket b owns sorted entries [start[b], start[b+1]).
 //   4. accumulate: one thread per bucket, XYZZ += affine (8M+2S), table points fetched with
 //                 128-bit loads; buckets above `heavy_cap` entries (adversarial inputs: all-equal
@@ -70,7 +71,7 @@ __global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, uint64_t tota
 // ---- 1-3 in one: counting sort ------------------------------------------------------------------
 // The keys are bucket numbers, at most 2^16 distinct values, so no radix passes are needed: count, scan, scatter.
 //   k_digit_count   recodes every scalar and adds one to count[bucket] per non-zero digit (global RED, no return value);
-//   k_bucket_scan   one block: exclusive scan of the counts -> start[0..M] and the scatter cursors;
+//   k_bucket_tile_totals + k_bucket_scan   exclusive scan of the counts over tiles of 1024 -> start[0..M] and the scatter cursors;
 //   k_digit_scatter recodes again (32 B of scalar re-read per point instead of 64 B of digits written and read back) and
 //                   reserves each entry's slot in its bucket's run with one ATOM: vals[slot] = table index | sign.
 // Zero digits simply vanish (the radix path parks them in a discard bucket).  Entries of a bucket arrive in whatever
