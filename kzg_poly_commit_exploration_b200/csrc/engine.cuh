@@ -18,6 +18,7 @@ enum ScratchSlot {
   SCR_XYZZ_TMP, SCR_PREFIX, SCR_QUOT, SCR_SEG, SCR_OUT, SCR_MISC, SCR_FR_A, SCR_FR_B,
   SCR_BATCH_PTS, SCR_BATCH_AFF, SCR_PARTIALS, SCR_HEAVY_PARTS,
   SCR_TREE_A, SCR_TREE_B, SCR_TREE_PREFIX, SCR_TREE_TOT, SCR_TREE_SEG, SCR_TREE_IOTA, SCR_ORDER,
+  SCR_L2_A, SCR_L2_B, SCR_L2_PREFIX, SCR_L2_TOT, SCR_L2_SEG, SCR_L2_IOTA, SCR_L2_START, SCR_L2_VALS, SCR_L2_MISC,
   SCR_COUNT
 };
 
@@ -72,6 +73,8 @@ struct kzg_ctx {
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_tree_k = 0;                  // pairs per thread in the halving rounds: 0 = auto (fill the last wave), else 8..16
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
+  int opt_msm_l2 = -1;                 // bucket sums reduced as a second bucket problem (msm.cu finish_level2): 0 off, 1 on, -1 = by window (on from 18 bits)
+  int opt_l2_rounds = -1;              // affine halving rounds of that second problem, -1 = auto
   int opt_reduce_lk = -1;              // level 1 of the bucket reduction: log2 of the buckets a lane walks serially (msm_tail.cu k_reduce_l1k); -1 = auto
   int opt_acc_minblocks = 0;           // resident blocks per SM the accumulate kernel is compiled for (0 = auto: 4 after halving rounds, else 3)
   int sm_count = 148;
@@ -271,7 +274,10 @@ int32_t batch_invert_inplace(kzg_ctx* ctx, Fq* v, uint64_t N, Fq* ws, uint64_t t
 // bounds start[0..M] over vals (table index | sign << 31).  Out: dense affine points + their bounds.
 int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const char* tab_pitched,
                         uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
-                        const uint32_t** seg_out, const uint32_t** iota_out, uint64_t* entries_out);
+                        const uint32_t** seg_out, const uint32_t** iota_out, uint64_t* entries_out,
+                        uint32_t tab_pitch = MSM_TAB_PITCH, int level = 1);
+// result[k] = 2^shift * res2[2k] + res2[2k + 1], k < calls (msm_tail.cu; the two halves of a second-level bucket reduction)
+int32_t combine_level2(kzg_ctx* ctx, const G1Xyzz* res2, int shift, int calls, G1Xyzz* results_dev);
 
 // ---- engine_one.cu: the single-device engine API (one_* = the kzg_* entry point of the same name on ONE device) ----
 int32_t one_ctx_create(kzg_ctx** out, int32_t device_id);

@@ -16,6 +16,7 @@
 //   5. reduce   : sum_b (b+1) * B_b by warp-level suffix scans, three fused launches (msm_tail.cu).
 // Integer-multiply bound: 3 000 wide multiply-adds per bucket addition, 96 B of HBM per addition.
 #include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
 #include "engine.cuh"
 
 namespace kzg {
@@ -359,6 +360,136 @@ int auto_tree_rounds(uint64_t entries) {
   return r;
 }
 
+// ---- level 2: the bucket sums reduced as a bucket problem of their own ----------------------------------------------
+// sum_d d * B_d over 2^(c-1) buckets costs the running-sum tail ~80 Fq products per bucket (msm_tail.cu), which is what
+// keeps the window at 17 bits.  Split the digit d = hi * 2^s + lo: sum_d d B_d = 2^s sum_hi hi H_hi + sum_lo lo L_lo with
+// H_hi = sum of the B_d with that hi, L_lo likewise — two bucket problems of 2^(c-1-s) and 2^s - 1 buckets whose POINTS
+// are the dense affine points the halving rounds of level 1 left (one or two per non-empty bucket), i.e. two affine
+// additions of ~6 products per level-1 point instead of a share of the tail.  The points are addressed by position
+// (pitch 96) exactly as level 1 addresses the table, so the same kernels run the level-2 halving rounds, the (now tiny)
+// accumulate and the fused tail over 2 x calls sets of 2^(c-1-s) buckets; combine_level2 adds the two halves.
+__global__ void __launch_bounds__(256)
+k_l2_count(const uint32_t* __restrict__ seg, uint32_t Mtot, uint32_t half, uint32_t s_lo, uint32_t MS,
+           uint32_t* __restrict__ cnt, uint32_t* __restrict__ off_lo) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= Mtot) return;
+  const uint32_t call = b / half, d = b % half + 1;
+  const uint32_t hi = d >> s_lo, lo = d & ((1u << s_lo) - 1u);
+  if (lo == 0) {
+    // d = hi * 2^s: the first bucket of its hi group, whose points are the contiguous range up to d + 2^s (no atomics:
+    // neighbouring buckets share hi and would serialise on one counter)
+    const uint32_t end = min(b + (1u << s_lo), (call + 1) * half);
+    cnt[(size_t)(call * 2) * MS + (hi - 1)] = __ldg(seg + end) - __ldg(seg + b);
+    return;
+  }
+  const uint32_t len = __ldg(seg + b + 1) - __ldg(seg + b);
+  if (len) off_lo[b] = atomicAdd(cnt + (size_t)(call * 2 + 1) * MS + (lo - 1), len);
+}
+__global__ void __launch_bounds__(256)
+k_l2_fill(const uint32_t* __restrict__ seg, uint32_t Mtot, uint32_t half, uint32_t s_lo, uint32_t MS,
+          const uint32_t* __restrict__ start2, const uint32_t* __restrict__ off_lo, uint32_t* __restrict__ vals2) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= Mtot) return;
+  const uint32_t p0 = __ldg(seg + b), len = __ldg(seg + b + 1) - p0;
+  if (!len) return;
+  const uint32_t call = b / half, d = b % half + 1;
+  const uint32_t hi = d >> s_lo, lo = d & ((1u << s_lo) - 1u);
+  if (hi) {                                         // position inside the hi group = distance from the group's first point
+    const uint32_t at = __ldg(start2 + (size_t)(call * 2) * MS + (hi - 1)) + (p0 - __ldg(seg + (b - lo)));
+    for (uint32_t i = 0; i < len; i++) vals2[at + i] = p0 + i;
+  }
+  if (lo) {
+    const uint32_t at = __ldg(start2 + (size_t)(call * 2 + 1) * MS + (lo - 1)) + off_lo[b];
+    for (uint32_t i = 0; i < len; i++) vals2[at + i] = p0 + i;
+  }
+}
+
+// seg[0..Mtot] = bounds of the dense points `dense` (at most E_bound of them) over Mtot = calls * half level-1 buckets
+static int32_t finish_level2(kzg_ctx* ctx, const uint32_t* seg, const G1Affine* dense, uint64_t E_bound, uint32_t half,
+                             int calls, int c, G1Xyzz* results_dev) {
+  const uint32_t Mtot = half * (uint32_t)calls;
+  const uint32_t s_lo = (uint32_t)(c - 1) / 2, MS = 1u << ((uint32_t)(c - 1) - s_lo);
+  const uint32_t sets = 2u * (uint32_t)calls, M2 = sets * MS;
+  const uint64_t E2 = 2 * E_bound;
+  if (E2 >= (1ull << 31)) return fail(ctx, KZG_E_BAD_ARG, "second-level bucket problem too large");
+  void *st2, *misc, *v2;
+  KZG_TRY(scratch_get(ctx, SCR_L2_START, ((size_t)M2 + 3) * 4, &st2));
+  KZG_TRY(scratch_get(ctx, SCR_L2_MISC, ((size_t)M2 * 2 + 8 + SCAN_TILE + (size_t)Mtot) * 4, &misc));
+  KZG_TRY(scratch_get(ctx, SCR_L2_VALS, (E2 + 16) * 4, &v2));
+  uint32_t* start2 = reinterpret_cast<uint32_t*>(st2);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(misc);
+  uint32_t* cursor = cnt + M2 + 4;
+  uint32_t* off = cursor + M2 + 2 + SCAN_TILE;
+  uint32_t* vals2 = reinterpret_cast<uint32_t*>(v2);
+  KZG_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, (size_t)M2 * 4, ctx->stream));
+  k_l2_count<<<blocks_for(Mtot, 256), 256, 0, ctx->stream>>>(seg, Mtot, half, s_lo, MS, cnt, off);
+  KZG_LAUNCHED(ctx);
+  KZG_TRY(launch_bucket_scan(ctx, cnt, M2, start2, cursor));
+  k_l2_fill<<<blocks_for(Mtot, 256), 256, 0, ctx->stream>>>(seg, Mtot, half, s_lo, MS, start2, off, vals2);
+  KZG_LAUNCHED(ctx);
+
+  // level-2 halving rounds until a bucket holds ~16 points (the accumulate then splits it over a few threads)
+  int rounds2 = ctx->opt_l2_rounds;
+  if (rounds2 < 0) {      // down to ~16 points per bucket, but no rounds of under 2^16 pairs (their inversion chain costs more than the accumulate)
+    const uint64_t stop = std::max<uint64_t>(16ull * M2, 1ull << 17);
+    rounds2 = 0;
+    while (rounds2 < 14 && (E2 >> rounds2) > stop) rounds2++;
+  }
+  const uint32_t* acc_start = start2;
+  const uint32_t* acc_vals = vals2;
+  const char* acc_tab = reinterpret_cast<const char*>(dense);
+  uint64_t acc_entries = E2;
+  if (rounds2 > 0) {
+    const G1Affine* d2 = nullptr;
+    KZG_TRY(msm_tree_rounds(ctx, start2, vals2, reinterpret_cast<const char*>(dense), M2, E2, rounds2, &d2, &acc_start,
+                            &acc_vals, &acc_entries, DENSE_PITCH, 2));
+    acc_tab = reinterpret_cast<const char*>(d2);
+  }
+  uint32_t logT = 0;
+  while (((uint64_t)M2 << logT) < (1u << 17) && acc_entries / ((uint64_t)M2 << logT) > 8 && logT < 6) logT++;
+  void *parts, *hv, *hp, *r2;
+  KZG_TRY(scratch_get(ctx, SCR_PARTIALS, ((size_t)M2 << logT) * sizeof(G1Xyzz), &parts));
+  const uint32_t heavy_cap = (uint32_t)ctx->opt_heavy_cap;
+  const size_t heavy_max = E2 / heavy_cap + 2 + 64;
+  KZG_TRY(scratch_get(ctx, SCR_HEAVY, (heavy_max + 1) * 4, &hv));
+  uint32_t* heavy_count = reinterpret_cast<uint32_t*>(hv);
+  uint32_t* heavy_list = heavy_count + 1;
+  KZG_CUDA_OK(ctx, cudaMemsetAsync(heavy_count, 0, 4, ctx->stream));
+  const uint32_t* perm = nullptr;
+  if (ctx->opt_acc_order) {
+    void* pm;
+    KZG_TRY(scratch_get(ctx, SCR_ORDER, (size_t)M2 * 4 + 16, &pm));
+    k_bucket_order<<<1, 1024, 0, ctx->stream>>>(acc_start, M2, reinterpret_cast<uint32_t*>(pm));
+    KZG_LAUNCHED(ctx);
+    perm = reinterpret_cast<const uint32_t*>(pm);
+  }
+  k_bucket_acc<4><<<blocks_for((uint64_t)M2 << logT, 128), 128, 0, ctx->stream>>>(
+      acc_start, acc_vals, acc_tab, DENSE_PITCH, M2, logT, heavy_cap, perm, reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
+  KZG_LAUNCHED(ctx);
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  KZG_TRY(scratch_get(ctx, SCR_HEAVY_PARTS, heavy_max * HEAVY_BLOCKS * sizeof(G1Xyzz), &hp));
+  k_bucket_heavy<<<dim3(HEAVY_BLOCKS, 16), 128, 0, ctx->stream>>>(acc_start, acc_vals, acc_tab, DENSE_PITCH,
+                                                                 reinterpret_cast<G1Xyzz*>(hp), heavy_list, heavy_count);
+  KZG_LAUNCHED(ctx);
+  k_heavy_fold<<<8, 128, 0, ctx->stream>>>(reinterpret_cast<G1Xyzz*>(hp), logT, reinterpret_cast<G1Xyzz*>(parts), heavy_list, heavy_count);
+  KZG_LAUNCHED(ctx);
+  KZG_TRY(scratch_get(ctx, SCR_RED_A, ((size_t)sets + 4) * sizeof(G1Xyzz), &r2));
+  KZG_TRY(reduce_buckets_multi(ctx, reinterpret_cast<G1Xyzz*>(parts), MS, logT, (int)sets, reinterpret_cast<G1Xyzz*>(r2)));
+  KZG_TRY(combine_level2(ctx, reinterpret_cast<G1Xyzz*>(r2), (int)s_lo, calls, results_dev));
+  KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  return KZG_OK;
+}
+
+static inline bool use_level2(const kzg_ctx* ctx, int c) {
+  return ctx->opt_msm_l2 == 1 || (ctx->opt_msm_l2 < 0 && c >= 18);
+}
+// halving rounds of level 1 when level 2 follows: until a bucket holds about one point
+static inline int level1_rounds_for_l2(uint64_t total, uint32_t Mtot, int at_least) {
+  int r = at_least > 1 ? at_least : 1;
+  while (r < 12 && (total >> r) > (uint64_t)Mtot) r++;
+  return r;
+}
+
 int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev, uint64_t n,
                    G1Xyzz* result_dev) {
   if (n == 0) return set_infinity(ctx, result_dev, 1);
@@ -429,6 +560,8 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   uint32_t acc_pitch = MSM_TAB_PITCH;
   uint64_t acc_entries = total;
   int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds(total);
+  const bool l2 = use_level2(ctx, c);
+  if (l2) rounds = ctx->opt_msm_tree_rounds > 0 ? ctx->opt_msm_tree_rounds : level1_rounds_for_l2(total, half, rounds);
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   if (rounds > 0) {
     const G1Affine* dense = nullptr;
@@ -436,6 +569,7 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
                             &acc_entries));
     acc_tab = reinterpret_cast<const char*>(dense); acc_pitch = DENSE_PITCH;
   }
+  if (l2) return finish_level2(ctx, acc_start, reinterpret_cast<const G1Affine*>(acc_tab), acc_entries, half, 1, c, result_dev);
 
   // threads per bucket: aim for ~2^18 accumulate threads
   uint32_t logT = 0;
@@ -502,7 +636,7 @@ int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const*
   const uint64_t total = (uint64_t)W * n * (uint64_t)B;
   if ((uint64_t)W * s->n >= (1ull << 31) || total >= (1ull << 32))
     return fail(ctx, KZG_E_BAD_ARG, "msm too large for 31-bit table indices");
-  if (half > (1u << 18) || (uint64_t)M > (1ull << 20)) return fail(ctx, KZG_E_BAD_ARG, "fused calls: too many buckets (window too wide)");
+  if ((uint64_t)M > (1ull << 20)) return fail(ctx, KZG_E_BAD_ARG, "fused calls: too many buckets (window too wide)");
 
   void *vb, *st, *hv, *cc;
   KZG_TRY(scratch_get(ctx, SCR_VALS_B, total * 4, &vb));
@@ -534,12 +668,15 @@ int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const*
   uint32_t acc_pitch = MSM_TAB_PITCH;
   uint64_t acc_entries = total;
   int rounds = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds(total);
+  const bool l2 = use_level2(ctx, c);
+  if (l2) rounds = ctx->opt_msm_tree_rounds > 0 ? ctx->opt_msm_tree_rounds : level1_rounds_for_l2(total, M, rounds);
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   if (rounds > 0) {
     const G1Affine* dense = nullptr;
     KZG_TRY(msm_tree_rounds(ctx, acc_start, acc_vals, acc_tab, M, total, rounds, &dense, &acc_start, &acc_vals, &acc_entries));
     acc_tab = reinterpret_cast<const char*>(dense); acc_pitch = DENSE_PITCH;
   }
+  if (l2) return finish_level2(ctx, acc_start, reinterpret_cast<const G1Affine*>(acc_tab), acc_entries, half, B, c, results_dev);
   uint32_t logT = 0;
   if (ctx->opt_acc_split >= 0) logT = (uint32_t)ctx->opt_acc_split;
   else while (((uint64_t)M << logT) < (1u << 18) && acc_entries / ((uint64_t)M << logT) > (uint64_t)(rounds > 0 ? 8 : ctx->opt_acc_min_entries)) logT++;

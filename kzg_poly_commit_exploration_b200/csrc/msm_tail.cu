@@ -642,4 +642,23 @@ int32_t reduce_buckets_multi(kzg_ctx* ctx, const G1Xyzz* parts, uint32_t M, uint
   return KZG_OK;
 }
 
+// result[k] = 2^shift * res2[2k] + res2[2k + 1]: the hi and lo halves of a second-level bucket reduction (msm.cu)
+__global__ void __launch_bounds__(128)
+k_combine_l2(const G1Xyzz* __restrict__ res2, int shift, G1Xyzz* __restrict__ out) {
+  __shared__ CoopBuf sh;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  G1Xyzz acc = res2[2 * blockIdx.x];
+#pragma unroll 1
+  for (int k = 0; k < shift; k++) dbl4(acc, &sh, w, lane);
+  G1Xyzz lo = res2[2 * blockIdx.x + 1];
+  add4(acc, lo, true, &sh, w, lane);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+int32_t combine_level2(kzg_ctx* ctx, const G1Xyzz* res2, int shift, int calls, G1Xyzz* results_dev) {
+  k_combine_l2<<<(unsigned)calls, 128, 0, ctx->stream>>>(res2, shift, results_dev);
+  KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
 }  // namespace kzg

@@ -105,7 +105,7 @@ struct PairRef { const G1Affine* p1; const G1Affine* p2; bool n1, n2; };
 template <bool R1>
 __device__ __forceinline__ PairRef pair_ref(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out,
                                             const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src,
-                                            uint32_t b, uint32_t p) {
+                                            uint32_t b, uint32_t p, uint32_t pitch) {
   const uint32_t q = p - __ldg(seg_out + b);
   const uint32_t s = __ldg(seg_in + b), len = __ldg(seg_in + b + 1) - s;
   const uint32_t e1 = s + 2 * q;
@@ -113,10 +113,11 @@ __device__ __forceinline__ PairRef pair_ref(const uint32_t* __restrict__ seg_in,
   PairRef r;
   if (R1) {
     const uint32_t v1 = __ldg(vals + e1), v2 = has2 ? __ldg(vals + e1 + 1) : 0u;
-    // round 1 reads the folded-window table: one entry per 128-byte line (MSM_TAB_PITCH)
+    // round 1 gathers by index: the folded-window table (one entry per 128-byte line, MSM_TAB_PITCH), or the dense points
+    // of the first level when the bucket sums themselves are reduced as a second bucket problem (pitch 96, msm.cu)
     const char* tb = reinterpret_cast<const char*>(src);
-    r.p1 = reinterpret_cast<const G1Affine*>(tb + (size_t)(v1 & 0x7FFFFFFFu) * MSM_TAB_PITCH); r.n1 = (v1 >> 31) != 0;
-    r.p2 = has2 ? reinterpret_cast<const G1Affine*>(tb + (size_t)(v2 & 0x7FFFFFFFu) * MSM_TAB_PITCH) : nullptr;
+    r.p1 = reinterpret_cast<const G1Affine*>(tb + (size_t)(v1 & 0x7FFFFFFFu) * pitch); r.n1 = (v1 >> 31) != 0;
+    r.p2 = has2 ? reinterpret_cast<const G1Affine*>(tb + (size_t)(v2 & 0x7FFFFFFFu) * pitch) : nullptr;
     r.n2 = (v2 >> 31) != 0;
   } else {
     r.p1 = src + e1; r.n1 = false;
@@ -129,7 +130,7 @@ template <bool R1>
 __global__ void __launch_bounds__(128)
 k_seg_den(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
           const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
-          Fq* __restrict__ prefix, Fq* __restrict__ tot) {
+          Fq* __restrict__ prefix, Fq* __restrict__ tot, uint32_t pitch) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint32_t NP = __ldg(seg_out + M);
@@ -142,11 +143,13 @@ k_seg_den(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_
       const uint32_t p = (uint32_t)p0 + k;
       if (p >= NP) break;
       while (__ldg(seg_out + b + 1) <= p) b++;
-      PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p);
-      Fq d;
-      pair_den(d, r.p1, r.n1, r.p2, r.n2);
+      PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p, pitch);
       st_fq(prefix + (size_t)k * T + t, acc);
-      mul(acc, acc, d);
+      if (r.p2) {                                   // the last entry of an odd run passes through: d = 1, no product
+        Fq d;
+        pair_den(d, r.p1, r.n1, r.p2, r.n2);
+        mul(acc, acc, d);
+      }
     }
   }
   st_fq(tot + t, acc);
@@ -156,7 +159,7 @@ template <bool R1>
 __global__ void __launch_bounds__(128)
 k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
           const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
-          const Fq* __restrict__ prefix, Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
+          const Fq* __restrict__ prefix, Fq* __restrict__ tot_inv, G1Affine* __restrict__ out, uint32_t pitch) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint32_t NP = __ldg(seg_out + M);
@@ -177,7 +180,12 @@ k_seg_add(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_
 #pragma unroll 1
   for (int k = kmax - 1; k >= 0; k--) {
     const uint32_t p = (uint32_t)p0 + k;
-    PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, bk[k], p);
+    PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, bk[k], p, pitch);
+    if (!r.p2) {                                    // passes through (d = 1 in k_seg_den: the thread inverse is untouched)
+      G1Affine a; ld_point(a, r.p1, r.n1);
+      st_fq(&out[p].x, a.x); st_fq(&out[p].y, a.y);
+      continue;
+    }
     Fq d, pf, dinv;
     pair_den(d, r.p1, r.n1, r.p2, r.n2);
     ld_fq_plain(pf, prefix + (size_t)k * T + t);
@@ -211,7 +219,7 @@ template <bool R1, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_seg_add_lean(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
                const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
-               const Fq* __restrict__ prefix, Fq* __restrict__ tot_inv, G1Affine* __restrict__ out) {
+               const Fq* __restrict__ prefix, Fq* __restrict__ tot_inv, G1Affine* __restrict__ out, uint32_t pitch) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint32_t NP = __ldg(seg_out + M);
@@ -224,9 +232,15 @@ k_seg_add_lean(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__
   for (int k = kmax - 1; k >= 0; k--) {
     const uint32_t p = (uint32_t)p0 + k;
     while (__ldg(seg_out + b) > p) b--;            // the bucket of p: positions are walked downwards
-    const PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p);
+    const PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p, pitch);
+    if (r.p2 == nullptr) {                          // the last entry of an odd run passes through: a copy, no product
+      Fq x, y; ld_fq_plain(x, &r.p1->x); ld_fq_plain(y, &r.p1->y);   // (d = 1 in k_seg_den: the thread inverse is untouched)
+      if (R1) { Fq m; neg(m, y); if (r.n1 && !(is_zero(x) && is_zero(y))) y = m; }
+      st_fq(&out[p].x, x); st_fq(&out[p].y, y);
+      continue;
+    }
     Fq d, dinv;
-    bool rare = r.p2 == nullptr;
+    bool rare = false;
     if (!rare) {
       Fq x1; ld_fq_plain(x1, &r.p1->x); ld_fq_plain(d, &r.p2->x);
       rare = is_zero(x1) || is_zero(d);            // x = 0 may be the infinity marker
@@ -271,17 +285,23 @@ static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((
 // costs 6 % (profiles/sweep_carve_r02.txt): not kept.
 template <bool R1>
 static void launch_seg_add(kzg_ctx* ctx, unsigned grid, const uint32_t* seg_in, const uint32_t* so, uint32_t M, const uint32_t* vals,
-                           const G1Affine* src, uint64_t T, int K, const Fq* prefix, Fq* tot, G1Affine* out) {
+                           const G1Affine* src, uint64_t T, int K, const Fq* prefix, Fq* tot, G1Affine* out, uint32_t pitch) {
   const int lean = R1 ? ctx->opt_tree_lean_r1 : ctx->opt_tree_lean;
-  if (lean == 6) k_seg_add_lean<R1, 6><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
-  else if (lean == 5) k_seg_add_lean<R1, 5><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
-  else if (lean == 4) k_seg_add_lean<R1, 4><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
-  else k_seg_add<R1><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out);
+  if (lean == 6) k_seg_add_lean<R1, 6><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out, pitch);
+  else if (lean == 5) k_seg_add_lean<R1, 5><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out, pitch);
+  else if (lean == 4) k_seg_add_lean<R1, 4><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out, pitch);
+  else k_seg_add<R1><<<grid, 128, 0, ctx->stream>>>(seg_in, so, M, vals, src, T, K, prefix, tot, out, pitch);
 }
 
 int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t* vals_dev, const char* tab_pitched,
                         uint32_t M, uint64_t entries, int rounds, const G1Affine** pts_out,
-                        const uint32_t** seg_out_p, const uint32_t** iota_out, uint64_t* entries_out) {
+                        const uint32_t** seg_out_p, const uint32_t** iota_out, uint64_t* entries_out,
+                        uint32_t tab_pitch, int level) {
+  // level 1: the scratch arenas SCR_TREE_*; level 2 (the bucket sums of level 1 reduced as a bucket problem of their own,
+  // msm.cu finish_level2) reads level 1's arenas while it runs, so it has a set of its own
+  const int sA = level == 2 ? SCR_L2_A : SCR_TREE_A, sB = level == 2 ? SCR_L2_B : SCR_TREE_B;
+  const int sPF = level == 2 ? SCR_L2_PREFIX : SCR_TREE_PREFIX, sTW = level == 2 ? SCR_L2_TOT : SCR_TREE_TOT;
+  const int sSG = level == 2 ? SCR_L2_SEG : SCR_TREE_SEG, sIO = level == 2 ? SCR_L2_IOTA : SCR_TREE_IOTA;
   const uint64_t top = (uint64_t)ctx->opt_inv_top;
   // upper bounds on the number of points after each round (exact counts stay on the device)
   auto halve = [M](uint64_t e) { uint64_t h = (e + M) / 2 + 1; return h < e ? h : e; };   // never grows
@@ -289,14 +309,14 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
   const uint64_t e2 = halve(e1);
   const uint64_t T1 = (e1 + 8 - 1) / 8;            // most threads a round can have (K >= 8)
   void *A, *B, *PF, *TW, *SG, *IO;
-  KZG_TRY(scratch_get(ctx, SCR_TREE_A, e1 * sizeof(G1Affine), &A));
-  KZG_TRY(scratch_get(ctx, SCR_TREE_B, e2 * sizeof(G1Affine), &B));
-  KZG_TRY(scratch_get(ctx, SCR_TREE_PREFIX, (T1 * ST_K + 16) * sizeof(Fq), &PF));
-  KZG_TRY(scratch_get(ctx, SCR_TREE_TOT, (T1 + invert_scratch_elems(T1, top)) * sizeof(Fq), &TW));
+  KZG_TRY(scratch_get(ctx, sA, e1 * sizeof(G1Affine), &A));
+  KZG_TRY(scratch_get(ctx, sB, e2 * sizeof(G1Affine), &B));
+  KZG_TRY(scratch_get(ctx, sPF, (T1 * ST_K + 16) * sizeof(Fq), &PF));
+  KZG_TRY(scratch_get(ctx, sTW, (T1 + invert_scratch_elems(T1, top)) * sizeof(Fq), &TW));
   if (rounds > SEG_MAX_ROUNDS) rounds = SEG_MAX_ROUNDS;
   const uint32_t ntiles = (M + SEG_TILE - 1) / SEG_TILE;
   if (ntiles > SEG_TILE) return fail(ctx, KZG_E_BAD_ARG, "too many buckets for the halving rounds");
-  KZG_TRY(scratch_get(ctx, SCR_TREE_SEG, (size_t)rounds * ((size_t)M + 2 + ntiles) * 4, &SG));
+  KZG_TRY(scratch_get(ctx, sSG, (size_t)rounds * ((size_t)M + 2 + ntiles) * 4, &SG));
   Fq* prefix = reinterpret_cast<Fq*>(PF);
   Fq* tot = reinterpret_cast<Fq*>(TW);
   Fq* inv_ws = tot + T1;
@@ -324,26 +344,31 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
       const double per_slot = (double)bound * 1.004 / ((double)ctx->sm_count * bps * 128);
       int waves = (int)((per_slot + ST_K - 1e-9) / ST_K); if (waves < 1) waves = 1;
       K = (int)(per_slot / waves + 0.999999);
-      if (K < 8) K = 8;
+      // at least 8 pairs per thread in round 1 (the arenas hold e1 / 8 thread totals); a late round of under a wave may
+      // go down to 2: its threads then run 2 instead of 8 additions back to back (a lone warp needs ~7 us per addition)
+      int kmin = (int)((8.0 * (double)bound) / (double)e1 + 0.999999);
+      if (kmin < 2) kmin = 2;
+      if (kmin > 8) kmin = 8;
+      if (K < kmin) K = kmin;
       if (K > ST_K) K = ST_K;
       if (ctx->opt_tree_k >= 8 && ctx->opt_tree_k <= ST_K) K = ctx->opt_tree_k;
     }
     const uint64_t T = (bound + K - 1) / K;
     uint32_t* so = segs + (size_t)r * (M + 2);
     G1Affine* out = buf[r & 1];
-    if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot);
-    else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, K, prefix, tot);
+    if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot, tab_pitch);
+    else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, K, prefix, tot, 0);
     KZG_LAUNCHED(ctx);
     KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
     if (r == 0) {
-      KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
-      launch_seg_add<true>(ctx, blocks_for(T, 128), seg_in, so, M, vals_dev, src, T, K, prefix, tot, out);
-      KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
-    } else launch_seg_add<false>(ctx, blocks_for(T, 128), seg_in, so, M, nullptr, src, T, K, prefix, tot, out);
+      if (level == 1) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
+      launch_seg_add<true>(ctx, blocks_for(T, 128), seg_in, so, M, vals_dev, src, T, K, prefix, tot, out, tab_pitch);
+      if (level == 1) KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev_k[1], ctx->stream));
+    } else launch_seg_add<false>(ctx, blocks_for(T, 128), seg_in, so, M, nullptr, src, T, K, prefix, tot, out, 0);
     KZG_LAUNCHED(ctx);
     seg_in = so; src = out;
   }
-  KZG_TRY(scratch_get(ctx, SCR_TREE_IOTA, (bound + 16) * 4, &IO));
+  KZG_TRY(scratch_get(ctx, sIO, (bound + 16) * 4, &IO));
   k_iota<<<blocks_for(bound, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(IO), bound);
   KZG_LAUNCHED(ctx);
   *pts_out = src; *seg_out_p = seg_in; *iota_out = reinterpret_cast<uint32_t*>(IO); *entries_out = bound;

@@ -185,3 +185,36 @@ def test_fused_calls_on_a_group_context(native):
     s1.close(); one.close()
     sg.close()
     g.close()
+
+
+@pytest.mark.parametrize("window,coalesce,n", [(12, 1, 30000), (17, 2, 1 << 16), (19, 4, 1 << 17), (20, 2, 1 << 17)])
+def test_second_level_bucket_reduction(window, coalesce, n):
+    """option msm_l2 (msm.cu finish_level2; automatic from 18-bit windows on): the bucket sums of level 1 are reduced as a
+    second bucket problem (digit = hi * 2^s + lo).  Same bytes as the running-sum tail and as the known-secret identity,
+    alone and fused, uniform and adversarial scalars (one bucket per window: the heavy path of both levels)."""
+    import torch
+    ref_ctx = _ctx(1, 1)
+    s_ref = ref_ctx.setup_generate(SECRET, n)
+    r = O.R
+    sets = [util.scalar_stream_bytes(0xB0 + i, n) for i in range(3)]
+    sets.append(util.le(0x0123456789ABCDEF0123456789ABCDEF % r) * n)             # all equal
+    sets.append(b"".join(util.le((r - 1 - i) % r) for i in range(n)))            # just below r: folded to small values
+    expect = [ref_ctx.msm_g1(s_ref, s) for s in sets]
+    assert expect[0] == O.g1_compress(O.commit_known_secret(util.to_ints(sets[0]), S))
+    ctx = _ctx(2, coalesce)
+    ctx.set_option("msm_window_bits", window)
+    ctx.set_option("msm_l2", 1)
+    setup = ctx.setup_generate(SECRET, n)
+    for k, s in enumerate(sets):
+        assert ctx.msm_g1(setup, s) == expect[k], ("one-shot", k)
+    devs = [torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda() for s in sets]
+    torch.cuda.synchronize()
+    ts = [ctx.msm_g1_submit_dev(setup, d.data_ptr(), n) for d in devs[:2 * coalesce]]
+    for k, t in enumerate(ts):
+        assert ctx.msm_g1_wait(t) == expect[k], ("in flight", k)
+    ts = [ctx.msm_g1_submit(setup, s) for s in (sets[3], sets[0], sets[4], sets[3])[:2 * coalesce]]
+    want = [expect[3], expect[0], expect[4], expect[3]]
+    for k, t in enumerate(ts):
+        assert ctx.msm_g1_wait(t) == want[k], ("adversarial in flight", k)
+    setup.close(); ctx.close()
+    s_ref.close(); ref_ctx.close()
