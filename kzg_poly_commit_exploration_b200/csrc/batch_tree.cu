@@ -63,10 +63,14 @@ k_r1_den(const uint8_t* __restrict__ scalars, uint64_t rows, uint64_t n, uint64_
 #pragma unroll 1
   for (int m = 0; m < KP; m++) {
     const uint32_t d1 = dig[2 * m], d2 = (2 * m + 1 < W) ? dig[2 * m + 1] : 0u;
-    Fq d;
-    pair_den(d, tab_entry(fix, i, W, c, 2 * m, d1), (d1 >> 31) != 0, tab_entry(fix, i, W, c, 2 * m + 1, d2), (d2 >> 31) != 0);
+    const G1Affine* p1 = tab_entry(fix, i, W, c, 2 * m, d1);
+    const G1Affine* p2 = tab_entry(fix, i, W, c, 2 * m + 1, d2);
     st_fq(prefix + (size_t)m * T + t, acc);
-    mul(acc, acc, d);
+    if (p1 && p2) {               // the unpaired last lookup (odd W) and zero digits pass through: d = 1, no product
+      Fq d;
+      pair_den(d, p1, (d1 >> 31) != 0, p2, (d2 >> 31) != 0);
+      mul(acc, acc, d);
+    }
   }
   st_fq(tot + t, acc);
 }
@@ -87,6 +91,13 @@ k_r1_add(const uint8_t* __restrict__ scalars, uint64_t rows, uint64_t n, uint64_
     const uint32_t d1 = dig[2 * m], d2 = (2 * m + 1 < W) ? dig[2 * m + 1] : 0u;
     const G1Affine* p1 = tab_entry(fix, i, W, c, 2 * m, d1);
     const G1Affine* p2 = tab_entry(fix, i, W, c, 2 * m + 1, d2);
+    if (!p1 || !p2) {             // passes through (d = 1 in k_r1_den: the thread inverse is untouched)
+      G1Affine a;
+      ld_point(a, p1 ? p1 : p2, ((p1 ? d1 : d2) >> 31) != 0);
+      G1Affine* dst = out + (size_t)(row * n + i) * KP + m;
+      st_fq(&dst->x, a.x); st_fq(&dst->y, a.y);
+      continue;
+    }
     Fq d, pf, dinv;
     pair_den(d, p1, (d1 >> 31) != 0, p2, (d2 >> 31) != 0);
     ld_fq_plain(pf, prefix + (size_t)m * T + t);

@@ -591,7 +591,13 @@ static int32_t flush_open_group(kzg_ctx* ctx) {
     } else {
       const uint8_t* ptrs[KZG_MAX_COALESCE];
       for (int k = 0; k < B; k++) ptrs[k] = q[k]->dev_scalars;
-      st = msm_bucket_multi(lane, s, ptrs, B, n, res);
+      // the bucket arrays of one problem hold at most 2^20 buckets: wide windows fuse fewer calls at a time
+      const uint64_t half = 1ull << (s->msm_c - 1);
+      const int per = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)B, (1ull << 20) / half));
+      for (int k0 = 0; k0 < B && st == KZG_OK; k0 += per) {
+        const int nb = std::min(per, B - k0);
+        st = nb == 1 ? msm_any(lane, s, ptrs[k0], n, res + k0) : msm_bucket_multi(lane, s, ptrs + k0, nb, n, res + k0);
+      }
     }
     lane->throughput_mode = false;
     KZG_TRY(st);

@@ -187,7 +187,7 @@ def test_fused_calls_on_a_group_context(native):
     g.close()
 
 
-@pytest.mark.parametrize("window,coalesce,n", [(12, 1, 30000), (17, 2, 1 << 16), (19, 4, 1 << 17), (20, 2, 1 << 17)])
+@pytest.mark.parametrize("window,coalesce,n", [(12, 1, 30000), (17, 2, 1 << 16), (19, 4, 1 << 17), (20, 2, 1 << 17), (20, 4, 1 << 15)])
 def test_second_level_bucket_reduction(window, coalesce, n):
     """option msm_l2 (msm.cu finish_level2; automatic from 18-bit windows on): the bucket sums of level 1 are reduced as a
     second bucket problem (digit = hi * 2^s + lo).  Same bytes as the running-sum tail and as the known-secret identity,
