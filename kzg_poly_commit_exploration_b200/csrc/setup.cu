@@ -324,9 +324,11 @@ int auto_msm_window(uint64_t n) {
   // run for throughput (5.75 instead of 10+ additions per bucket), and with it c = 17 (15 windows, 65536 buckets) wins
   // at n = 2^20: 5.06 -> 4.77 ms per MSM with eight calls in flight, two fused (profiles/sweep_coalesce_r02.txt); c = 18
   // leaves a 3-bit top window (n / 4 entries per bucket: the heavy path) and loses.
-  if (n >= (1ull << 20)) return 17;
-  if (n >= (1ull << 18)) return 16;
-  if (n >= (1ull << 17)) return 15;
+  // With pass-through entries free of products and late rounds of under a wave at 2-8 pairs per thread, short runs cost
+  // less and c = 17 also wins at 2^18 / 2^19 (2^19: 2.49 -> 2.40 ms fused, 3.71 -> 3.51 alone), c = 16 ties c = 15 at 2^17
+  // with a table one window smaller (profiles/sweep_coalesce_r02.txt (g)).
+  if (n >= (1ull << 18)) return 17;
+  if (n >= (1ull << 17)) return 16;
   int best = 4; double best_cost = 1e300;
   for (int c = 4; c <= 16; c++) {
     int W = windows_for(c);
