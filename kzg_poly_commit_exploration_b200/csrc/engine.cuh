@@ -39,6 +39,7 @@ struct kzg_ctx {
   uint64_t launches = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[3] = {0.f, 0.f, 0.f};
+  bool timers_stale = false;           // a wait finished a call whose phase events have not been read yet (one_ctx_last_kernel_ms does)
   cudaEvent_t ev_k[2] = {nullptr, nullptr};   // around the single dominant kernel of the last bulk call
   cudaEvent_t ev_t[2] = {nullptr, nullptr};
   void* scratch[kzg::SCR_COUNT] = {};

@@ -52,8 +52,9 @@ namespace {
 
 struct DeviceGuard {
   int prev = -1;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  bool changed = false;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) { cudaSetDevice(dev); changed = true; } }
+  ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
 };
 
 // value == 0 mod r  <=>  value in {0, r, 2r} (2^256 < 3r)
@@ -217,6 +218,12 @@ uint64_t one_ctx_launch_count(const kzg_ctx* ctx) {
 void* one_ctx_stream(const kzg_ctx* ctx) { return ctx ? reinterpret_cast<void*>(ctx->stream) : nullptr; }
 
 float one_ctx_last_kernel_ms(const kzg_ctx* ctx, int32_t which) {
+  if (ctx->timers_stale) {
+    kzg_ctx* c = const_cast<kzg_ctx*>(ctx);
+    DeviceGuard g(c->device);
+    update_timers(c);
+    c->timers_stale = false;
+  }
   return (which >= 0 && which <= 2) ? ctx->last_ms[which] : 0.f;
 }
 
@@ -394,7 +401,7 @@ uint64_t one_setup_g2_len(const kzg_setup* s) { return s ? s->g2_n : 0; }
 int32_t one_msm_plan(const kzg_ctx* ctx, const kzg_setup* s, uint64_t n, int32_t plan[5]) {
   if (!ctx || !s || !plan || !s->msm_c) return KZG_E_BAD_ARG;
   plan[0] = s->msm_c; plan[1] = s->msm_w; plan[2] = 1 << (s->msm_c - 1);
-  plan[3] = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds((uint64_t)s->msm_w * n);
+  plan[3] = ctx->opt_msm_tree_rounds >= 0 ? ctx->opt_msm_tree_rounds : auto_tree_rounds((uint64_t)s->msm_w * n);   // of a call on its own, first level
   plan[4] = (int32_t)MSM_TAB_PITCH;
   return KZG_OK;
 }
@@ -709,7 +716,7 @@ int32_t one_msm_g1_wait(kzg_ctx* ctx, int32_t ticket, uint8_t out_c48[48]) {
   KZG_CUDA_OK(ctx, cudaEventSynchronize(q.done));
   q.busy = false;
   ctx->last_lane = q.lane_index;
-  update_timers(ctx);
+  ctx->timers_stale = true;      // the phase timers are read when somebody asks (three event queries per wait add up: eight members per group wait)
   if (q.sharded) {
     uint32_t st;
     memcpy(&st, q.out_host + 48, 4);

@@ -240,8 +240,8 @@ k_seg_add_lean(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__
       continue;
     }
     Fq d, dinv;
-    bool rare = false;
-    if (!rare) {
+    bool rare;
+    {
       Fq x1; ld_fq_plain(x1, &r.p1->x); ld_fq_plain(d, &r.p2->x);
       rare = is_zero(x1) || is_zero(d);            // x = 0 may be the infinity marker
       sub(d, d, x1);
