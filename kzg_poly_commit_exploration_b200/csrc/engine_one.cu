@@ -910,8 +910,20 @@ static int32_t msm_batch_any(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* sc
   if (n == 0) return set_infinity(ctx, out, (uint32_t)blobs);   // empty sums: no table is touched (or built)
   if (s->fix_tab && n <= s->fix_n) return msm_fixed_batch(ctx, s, scalars_dev, blobs, n, stride, out);
   KZG_TRY(ensure_msm_table(ctx, s));
-  for (uint64_t b = 0; b < blobs; b++) KZG_TRY(msm_bucket(ctx, s, scalars_dev + b * stride * 32, n, out + b));
-  return KZG_OK;
+  // rows beyond the fixed-base table (long polynomials): up to four at a time as ONE bucket problem (msm_bucket_multi)
+  const uint64_t half = 1ull << (s->msm_c - 1);
+  const uint64_t per = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)KZG_MAX_COALESCE, (1ull << 20) / half));
+  const bool was = ctx->throughput_mode;
+  ctx->throughput_mode = was || blobs > 1;
+  int32_t st = KZG_OK;
+  for (uint64_t b = 0; b < blobs && st == KZG_OK; b += per) {
+    const int nb = (int)std::min<uint64_t>(per, blobs - b);
+    const uint8_t* ptrs[KZG_MAX_COALESCE];
+    for (int k = 0; k < nb; k++) ptrs[k] = scalars_dev + (b + (uint64_t)k) * stride * 32;
+    st = msm_bucket_multi(ctx, s, ptrs, nb, n, out + b);
+  }
+  ctx->throughput_mode = was;
+  return st;
 }
 
 // Rows are `n` coefficients apart; only the first `used` of a row can be non-zero (the rest is trailing-zero padding that

@@ -218,3 +218,21 @@ def test_second_level_bucket_reduction(window, coalesce, n):
         assert ctx.msm_g1_wait(t) == want[k], ("adversarial in flight", k)
     setup.close(); ctx.close()
     s_ref.close(); ref_ctx.close()
+
+
+def test_batches_of_long_rows_run_fused():
+    """kzg_commit_batch / kzg_open_batch with rows beyond the fixed-base table (long polynomials): rows go through the
+    bucket MSM four at a time as one problem — same bytes as one commit / open per row (src/polynomial.rs:200-215, 260-269)"""
+    ctx = _ctx(1, 1)
+    n, rows = 9000, 7
+    setup = ctx.setup_generate(SECRET, n)
+    coeffs = util.scalar_stream_bytes(0xD1, rows * n)
+    zs = util.scalar_stream_bytes(0xD2, rows)
+    one = [ctx.commit(setup, coeffs[r * n * 32:(r + 1) * n * 32]) for r in range(rows)]
+    assert one[0] == O.g1_compress(O.commit_known_secret(util.to_ints(coeffs[:n * 32]), S))
+    assert ctx.commit_batch(setup, coeffs, rows, n) == b"".join(one)
+    ys, proofs = ctx.open_batch(setup, coeffs, rows, n, zs)
+    for r in range(rows):
+        y, pr = ctx.open(setup, coeffs[r * n * 32:(r + 1) * n * 32], zs[r * 32:(r + 1) * 32])
+        assert ys[r * 32:(r + 1) * 32] == y and proofs[r * 48:(r + 1) * 48] == pr, r
+    setup.close(); ctx.close()
