@@ -74,6 +74,9 @@ struct kzg_ctx {
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_tree_k = 0;                  // pairs per thread in the halving rounds: 0 = auto (fill the last wave), else 8..16
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
+  int opt_den_side = 0;                // round-1 denominators of calls in flight as this many resident blocks per SM on a high-priority side stream (0 = off)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int opt_msm_l2 = -1;                 // bucket sums reduced as a second bucket problem (msm.cu finish_level2): 0 off, 1 on, -1 = by window (on from 18 bits)
   int opt_l2_rounds = -1;              // affine halving rounds of that second problem, -1 = auto
   int opt_reduce_lk = -1;              // level 1 of the bucket reduction: log2 of the buckets a lane walks serially (msm_tail.cu k_reduce_l1k); -1 = auto

@@ -173,6 +173,8 @@ void one_ctx_destroy(kzg_ctx* ctx) {
   for (int i = 0; i < 2; i++) if (ctx->ev_t[i]) cudaEventDestroy(ctx->ev_t[i]);
   for (int i = 0; i < 2; i++) if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
   for (int i = 0; i < 8; i++) if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+  for (int i = 0; i < 2; i++) if (ctx->side_ev[i]) cudaEventDestroy(ctx->side_ev[i]);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -241,6 +243,7 @@ int32_t one_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "coop_tail") ctx->opt_coop_tail = (int)value;
   else if (n == "reduce_lk") ctx->opt_reduce_lk = (int)value;
   else if (n == "msm_l2") ctx->opt_msm_l2 = (int)value;
+  else if (n == "den_side") ctx->opt_den_side = (int)std::min<int64_t>(8, std::max<int64_t>(0, value));
   else if (n == "l2_rounds") ctx->opt_l2_rounds = (int)value;
   else if (n == "tree_k") ctx->opt_tree_k = (int)value;
   else if (n == "p2p_timeout_ms") ctx->p2p_timeout_cycles = std::max<int64_t>(1, value) * (long long)ctx->sm_clock_khz;
@@ -472,7 +475,7 @@ void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
   dst->opt_tree_min_pairs = src->opt_tree_min_pairs; dst->opt_inv_top_fan = src->opt_inv_top_fan; dst->opt_inv_top = src->opt_inv_top;
   dst->opt_msm_tree_rounds = src->opt_msm_tree_rounds; dst->opt_acc_min_entries = src->opt_acc_min_entries;
   dst->opt_fixed_table_max_bytes = src->opt_fixed_table_max_bytes; dst->opt_setup_layout = src->opt_setup_layout;
-  dst->opt_setup_tree_min = src->opt_setup_tree_min; dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_reduce_lk = src->opt_reduce_lk; dst->opt_msm_l2 = src->opt_msm_l2; dst->opt_l2_rounds = src->opt_l2_rounds; dst->opt_acc_minblocks = src->opt_acc_minblocks;
+  dst->opt_setup_tree_min = src->opt_setup_tree_min; dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_reduce_lk = src->opt_reduce_lk; dst->opt_msm_l2 = src->opt_msm_l2; dst->opt_den_side = src->opt_den_side; dst->opt_l2_rounds = src->opt_l2_rounds; dst->opt_acc_minblocks = src->opt_acc_minblocks;
 }
 
 static void latch_queue(kzg_ctx* ctx) {

@@ -131,28 +131,31 @@ __global__ void __launch_bounds__(128)
 k_seg_den(const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_out, uint32_t M,
           const uint32_t* __restrict__ vals, const G1Affine* __restrict__ src, uint64_t T, int K,
           Fq* __restrict__ prefix, Fq* __restrict__ tot, uint32_t pitch) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
   const uint32_t NP = __ldg(seg_out + M);
-  Fq acc; set_one(acc);
-  const uint64_t p0 = t * K;
-  if (p0 < NP) {
-    uint32_t b = bucket_of(seg_out, M, (uint32_t)p0);
+  // grid-stride over the threads' worth of work: the usual launch has one block per 128 of them, the side-stream launch
+  // of round 1 (option den_side) a block or two per SM that stay resident beside another call's addition kernel
 #pragma unroll 1
-    for (int k = 0; k < K; k++) {
-      const uint32_t p = (uint32_t)p0 + k;
-      if (p >= NP) break;
-      while (__ldg(seg_out + b + 1) <= p) b++;
-      PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p, pitch);
-      st_fq(prefix + (size_t)k * T + t, acc);
-      if (r.p2) {                                   // the last entry of an odd run passes through: d = 1, no product
-        Fq d;
-        pair_den(d, r.p1, r.n1, r.p2, r.n2);
-        mul(acc, acc, d);
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+    Fq acc; set_one(acc);
+    const uint64_t p0 = t * K;
+    if (p0 < NP) {
+      uint32_t b = bucket_of(seg_out, M, (uint32_t)p0);
+#pragma unroll 1
+      for (int k = 0; k < K; k++) {
+        const uint32_t p = (uint32_t)p0 + k;
+        if (p >= NP) break;
+        while (__ldg(seg_out + b + 1) <= p) b++;
+        PairRef r = pair_ref<R1>(seg_in, seg_out, vals, src, b, p, pitch);
+        st_fq(prefix + (size_t)k * T + t, acc);
+        if (r.p2) {                                   // the last entry of an odd run passes through: d = 1, no product
+          Fq d;
+          pair_den(d, r.p1, r.n1, r.p2, r.n2);
+          mul(acc, acc, d);
+        }
       }
     }
+    st_fq(tot + t, acc);
   }
-  st_fq(tot + t, acc);
 }
 
 template <bool R1>
@@ -356,7 +359,24 @@ int32_t msm_tree_rounds(kzg_ctx* ctx, const uint32_t* start_dev, const uint32_t*
     const uint64_t T = (bound + K - 1) / K;
     uint32_t* so = segs + (size_t)r * (M + 2);
     G1Affine* out = buf[r & 1];
-    if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot, tab_pitch);
+    if (r == 0 && level == 1 && ctx->opt_den_side > 0 && ctx->throughput_mode && blocks_for(T, 128) > 4u * (unsigned)ctx->sm_count) {
+      // The round-1 denominators are a gather at the DRAM random-access rate with one product per pair: the multiplier idles.
+      // With calls in flight, run them as a few resident blocks per SM on a HIGH-priority side stream, so that they sit
+      // beside another lane's addition kernel (which keeps the other block slots) instead of owning the machine.
+      if (!ctx->side_stream) {
+        int lo = 0, hi = 0;
+        KZG_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        KZG_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+        KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
+        KZG_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->side_ev[1], cudaEventDisableTiming));
+      }
+      KZG_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[0], ctx->stream));
+      KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[0], 0));
+      k_seg_den<true><<<(unsigned)(ctx->sm_count * ctx->opt_den_side), 128, 0, ctx->side_stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot, tab_pitch);
+      KZG_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[1], ctx->side_stream));
+      KZG_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->side_ev[1], 0));
+    }
+    else if (r == 0) k_seg_den<true><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, vals_dev, src, T, K, prefix, tot, tab_pitch);
     else k_seg_den<false><<<blocks_for(T, 128), 128, 0, ctx->stream>>>(seg_in, so, M, nullptr, src, T, K, prefix, tot, 0);
     KZG_LAUNCHED(ctx);
     KZG_TRY(batch_invert_inplace(ctx, tot, T, inv_ws, top));
