@@ -51,7 +51,7 @@ struct kzg_ctx {
   int opt_msm_window = 0;              // 0 = auto
   int opt_fixed_window = 0;            // 0 = auto: the widest window whose table fits the memory budget (setup.cu auto_fixed_window)
   int64_t opt_fixed_table_max_bytes = 0;   // budget of that choice; 0 = 66 % of the device memory free at the time
-  int opt_msm_sort = -1;               // bucket sort of the MSM entries: 0 / -1 = counting sort (count / tiled scan / scatter), 1 = cub radix sort (kept for comparison)
+  int opt_msm_sort = -1;               // bucket sort of the MSM entries: 0 / -1 = counting sort (count / tiled scan / scatter), 1 = cub radix sort, 2 = two-level partition sort (both kept for comparison)
   int opt_acc_order = 1;               // hand the buckets to k_bucket_acc sorted by length (k_bucket_order)
   int opt_tree_lean = 4;               // pair-addition kernel of the dense halving rounds: 0 = points held in registers, 4 / 5 / 6 = reloading variant at that many blocks per SM
   int opt_tree_lean_r1 = 4;            // the same for round 1 (table gathers)

@@ -190,6 +190,183 @@ k_digit_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint
   }
 }
 
+// ---- 1-3 in one, two levels: partition sort ----------------------------------------------------------------------
+// The counting sort above pays two GLOBAL atomics per entry (a RED to count, an ATOM to reserve the slot): 21 ps per entry,
+// bound by the L2 atomic units.  Here the buckets are first split into PARTITIONS of 512 consecutive buckets:
+//   k_part_count    per block of 256 scalars a shared-memory histogram over the partitions, then one global RED per
+//                   (block, non-empty partition) instead of one per entry;
+//   k_part_scan     one block: partition bounds;
+//   k_part_scatter  the same histogram again, one global ATOM per (block, partition) reserves the block's range in the
+//                   partition, shared-memory atomics hand out the slots inside it: (bucket mod 512, table index | sign) as
+//                   one 8-byte record per entry, written in runs of ~15 per partition and block;
+//   k_part_sort     one block per partition (~60 k records): histogram of its 512 buckets in shared memory -> their
+//                   bounds (start[]) -> records scattered into the final entry order, all atomics in shared memory.
+// Same contract as the counting sort: start[0..M], vals in bucket order (any order inside a bucket), zero digits vanish.
+// MEASURED (profiles/sweep_coalesce_r02.txt (h), two fused calls at n = 2^20, 31.5 M entries): k_part_count 65 us (the
+// counting sort's count: 214), but k_part_scatter 352 and k_part_sort 304 — the 8-byte records land in runs of ~15 per
+// block and partition, and the final 4-byte scatter of 256 partitions x 492 KB works in a set the size of the L2 — 723 us
+// against 672 for the counting sort.  Kept behind option msm_sort = 2; smaller partitions staged through shared memory
+// would be the next step.
+constexpr int PART_LOG = 9;                     // buckets per partition (log2)
+constexpr uint32_t PART_W = 1u << PART_LOG;
+constexpr int PART_MAX = 2048;                  // partitions (M <= 2^20 buckets)
+
+__global__ void __launch_bounds__(256)
+k_part_count(ScalarPtrs sp, uint64_t n, int c, int W, uint32_t half, uint32_t* __restrict__ part_cnt) {
+  __shared__ uint32_t hist[PART_MAX];
+  const uint32_t np_call = half >> PART_LOG;                       // partitions of one call
+  for (uint32_t k = threadIdx.x; k < np_call; k += 256) hist[k] = 0;
+  __syncthreads();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    Fr k; ld_scalar(k, sp.p[blockIdx.y] + i * 32);
+    fr_canon_reduce(k);
+    SignedDigits sd; sd.init(k, c);
+#pragma unroll 1
+    for (int j = 0; j < W; j++) {
+      bool neg;
+      const uint32_t d = sd.next(j, &neg);
+      if (d) atomicAdd(&hist[(d - 1) >> PART_LOG], 1u);
+    }
+  }
+  __syncthreads();
+  part_cnt += (size_t)blockIdx.y * np_call;
+  for (uint32_t k = threadIdx.x; k < np_call; k += 256) if (hist[k]) atomicAdd(part_cnt + k, hist[k]);
+}
+
+// NP <= PART_MAX counts -> part_start[0..NP] and the scatter cursors; one block of 1024 threads, two counts per thread
+__global__ void __launch_bounds__(1024)
+k_part_scan(const uint32_t* __restrict__ part_cnt, uint32_t NP, uint32_t* __restrict__ part_start, uint32_t* __restrict__ part_cur) {
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t a0 = 2 * threadIdx.x < NP ? part_cnt[2 * threadIdx.x] : 0u;
+  const uint32_t a1 = 2 * threadIdx.x + 1 < NP ? part_cnt[2 * threadIdx.x + 1] : 0u;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = a0 + a1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += t; }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = warp_tot[lane], xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= (uint32_t)d) xi += t; }
+    warp_tot[lane] = xi - x;
+  }
+  __syncthreads();
+  const uint32_t ex = warp_tot[w] + inc - (a0 + a1);
+  if (2 * threadIdx.x < NP) { part_start[2 * threadIdx.x] = ex; part_cur[2 * threadIdx.x] = ex; }
+  if (2 * threadIdx.x + 1 < NP) { part_start[2 * threadIdx.x + 1] = ex + a0; part_cur[2 * threadIdx.x + 1] = ex + a0; }
+  if (threadIdx.x == 1023) part_start[NP] = ex + a0 + a1;      // the last thread's running sum is the grand total
+}
+
+__global__ void __launch_bounds__(256)
+k_part_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint32_t half,
+               uint32_t* __restrict__ part_cur, uint2* __restrict__ rec) {
+  __shared__ uint32_t hist[PART_MAX];      // counts, then the block's base inside each partition, then the running slot
+  const uint32_t np_call = half >> PART_LOG;
+  for (uint32_t k = threadIdx.x; k < np_call; k += 256) hist[k] = 0;
+  __syncthreads();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fr k;
+  if (i < n) {
+    ld_scalar(k, sp.p[blockIdx.y] + i * 32);
+    fr_canon_reduce(k);
+    SignedDigits sd; sd.init(k, c);
+#pragma unroll 1
+    for (int j = 0; j < W; j++) {
+      bool neg;
+      const uint32_t d = sd.next(j, &neg);
+      if (d) atomicAdd(&hist[(d - 1) >> PART_LOG], 1u);
+    }
+  }
+  __syncthreads();
+  part_cur += (size_t)blockIdx.y * np_call;
+  for (uint32_t q = threadIdx.x; q < np_call; q += 256) {
+    const uint32_t h = hist[q];
+    hist[q] = h ? atomicAdd(part_cur + q, h) : 0u;               // this block's range in partition q starts here
+  }
+  __syncthreads();
+  if (i < n) {
+    SignedDigits sd; sd.init(k, c);
+#pragma unroll 1
+    for (int j = 0; j < W; j++) {
+      bool neg;
+      const uint32_t d = sd.next(j, &neg);
+      if (!d) continue;
+      const uint32_t slot = atomicAdd(&hist[(d - 1) >> PART_LOG], 1u);
+      rec[slot] = make_uint2((uint32_t)((uint64_t)j * n_stride + i) | (neg ? 0x80000000u : 0u), (d - 1) & (PART_W - 1u));
+    }
+  }
+}
+
+// one block per partition: records [part_start[P], part_start[P+1]) -> start[P * 512 .. ] and vals in bucket order
+__global__ void __launch_bounds__(1024)
+k_part_sort(const uint2* __restrict__ rec, const uint32_t* __restrict__ part_start, uint32_t NP,
+            uint32_t* __restrict__ start, uint32_t* __restrict__ vals) {
+  __shared__ uint32_t cnt[PART_W];
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t P = blockIdx.x;
+  const uint32_t lo = __ldg(part_start + P), hi = __ldg(part_start + P + 1);
+  if (threadIdx.x < PART_W) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t e = lo + threadIdx.x; e < hi; e += 1024) atomicAdd(&cnt[rec[e].y], 1u);
+  __syncthreads();
+  // exclusive scan of the 512 counts by the first 512 threads (16 warps)
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t own = threadIdx.x < PART_W ? cnt[threadIdx.x] : 0u, inc = own;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += t; }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = warp_tot[lane], xi = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= (uint32_t)d) xi += t; }
+    warp_tot[lane] = xi - x;
+  }
+  __syncthreads();
+  if (threadIdx.x < PART_W) {
+    const uint32_t ex = lo + warp_tot[w] + inc - own;
+    start[(size_t)P * PART_W + threadIdx.x] = ex;
+    cnt[threadIdx.x] = ex;                                       // running slot of the bucket
+  }
+  if (P == NP - 1 && threadIdx.x == 0) start[(size_t)NP * PART_W] = hi;
+  __syncthreads();
+  for (uint32_t e = lo + threadIdx.x; e < hi; e += 1024) {
+    const uint2 r = rec[e];
+    vals[atomicAdd(&cnt[r.y], 1u)] = r.x;
+  }
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs);
+// buckets of the calls sp.p[0..B) (half each) -> start[0 .. B * half], vals; false if the geometry does not fit (the caller
+// then takes the counting sort)
+static bool part_sort_fits(uint32_t half, int B) {
+  const uint64_t M = (uint64_t)half * (uint64_t)B;
+  return half >= 8 * PART_W && (M >> PART_LOG) <= (uint64_t)PART_MAX;
+}
+static int32_t launch_part_sort(kzg_ctx* ctx, const ScalarPtrs& sp, int B, uint64_t n, int c, int W, uint64_t n_stride,
+                                uint32_t half, uint64_t total, uint32_t* start, uint32_t* vals) {
+  const uint32_t M = half * (uint32_t)B, NP = M >> PART_LOG;
+  void *pc, *rc;
+  KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)NP * 3 + 16) * 4, &pc));
+  KZG_TRY(scratch_get(ctx, SCR_KEYS_B, (total + 16) * 8, &rc));
+  uint32_t* part_cnt = reinterpret_cast<uint32_t*>(pc);
+  uint32_t* part_start = part_cnt + NP + 4;
+  uint32_t* part_cur = part_start + NP + 4;
+  KZG_CUDA_OK(ctx, cudaMemsetAsync(part_cnt, 0, (size_t)NP * 4, ctx->stream));
+  const dim3 grid(blocks_for(n, 256), (unsigned)B);
+  k_part_count<<<grid, 256, 0, ctx->stream>>>(sp, n, c, W, half, part_cnt);
+  KZG_LAUNCHED(ctx);
+  k_part_scan<<<1, 1024, 0, ctx->stream>>>(part_cnt, NP, part_start, part_cur);
+  KZG_LAUNCHED(ctx);
+  k_part_scatter<<<grid, 256, 0, ctx->stream>>>(sp, n, c, W, n_stride, half, part_cur, reinterpret_cast<uint2*>(rc));
+  KZG_LAUNCHED(ctx);
+  k_part_sort<<<NP, 1024, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(rc), part_start, NP, start, vals);
+  KZG_LAUNCHED(ctx);
+  return KZG_OK;
+}
+
 // ---- 4. accumulate -----------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -514,8 +691,12 @@ int32_t msm_bucket(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* scalars_dev,
   // Counting sort at every size since the scan is tiled (two launches): 21 ps per entry at 31 M entries (two fused calls at
   // n = 2^20, profiles/launches_r02_fused_n20.csv) against 22 ps for recode + two radix passes + bounds at 16-bit keys —
   // and 17-bit keys (n >= 2^20) would cost the radix sort a third pass.  The cub path stays behind option msm_sort = 1.
-  const bool counting = ctx->opt_msm_sort <= 0;
-  if (counting) {
+  const bool counting = ctx->opt_msm_sort <= 0 || ctx->opt_msm_sort == 2;
+  if (ctx->opt_msm_sort == 2 && part_sort_fits(half, 1)) {
+    // two-level partition sort (option msm_sort = 2): shared-memory atomics instead of two global ones per entry
+    ScalarPtrs sp = {}; sp.p[0] = scalars_dev;
+    KZG_TRY(launch_part_sort(ctx, sp, 1, n, c, W, s->n, half, total, reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb)));
+  } else if (counting) {
     // counting sort: count -> scan -> scatter (see above); count[] and cursor[] share one small arena
     void* cc;
     KZG_TRY(scratch_get(ctx, SCR_KEYS_A, ((size_t)half * 2 + 8 + SCAN_TILE) * 4, &cc));
@@ -653,13 +834,17 @@ int32_t msm_bucket_multi(kzg_ctx* ctx, const kzg_setup* s, const uint8_t* const*
   KZG_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   ScalarPtrs sp = {};
   for (int b = 0; b < B; b++) sp.p[b] = scalars_dev[b];
-  KZG_CUDA_OK(ctx, cudaMemsetAsync(count, 0, (size_t)M * 4, ctx->stream));
-  k_digit_count<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, half, count);
-  KZG_LAUNCHED(ctx);
-  KZG_TRY(launch_bucket_scan(ctx, count, M, reinterpret_cast<uint32_t*>(st), cursor));
-  k_digit_scatter<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, s->n, half, cursor,
-                                                                                 reinterpret_cast<uint32_t*>(vb));
-  KZG_LAUNCHED(ctx);
+  if (ctx->opt_msm_sort == 2 && part_sort_fits(half, B)) {
+    KZG_TRY(launch_part_sort(ctx, sp, B, n, c, W, s->n, half, total, reinterpret_cast<uint32_t*>(st), reinterpret_cast<uint32_t*>(vb)));
+  } else {
+    KZG_CUDA_OK(ctx, cudaMemsetAsync(count, 0, (size_t)M * 4, ctx->stream));
+    k_digit_count<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, half, count);
+    KZG_LAUNCHED(ctx);
+    KZG_TRY(launch_bucket_scan(ctx, count, M, reinterpret_cast<uint32_t*>(st), cursor));
+    k_digit_scatter<<<dim3(blocks_for(n, 256), (unsigned)B), 256, 0, ctx->stream>>>(sp, n, c, W, s->n, half, cursor,
+                                                                                   reinterpret_cast<uint32_t*>(vb));
+    KZG_LAUNCHED(ctx);
+  }
   KZG_CUDA_OK(ctx, cudaMemsetAsync(heavy_count, 0, 4, ctx->stream));
 
   const uint32_t* acc_start = reinterpret_cast<uint32_t*>(st);

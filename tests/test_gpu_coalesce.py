@@ -236,3 +236,25 @@ def test_batches_of_long_rows_run_fused():
         y, pr = ctx.open(setup, coeffs[r * n * 32:(r + 1) * n * 32], zs[r * 32:(r + 1) * 32])
         assert ys[r * 32:(r + 1) * 32] == y and proofs[r * 48:(r + 1) * 48] == pr, r
     setup.close(); ctx.close()
+
+
+@pytest.mark.parametrize("sort", [1, 2])
+def test_alternative_bucket_sorts(sort):
+    """option msm_sort: 1 = cub radix sort (lone calls), 2 = two-level partition sort (shared-memory atomics) — kept for
+    comparison with the default counting sort; same bytes, alone and fused, uniform and all-equal scalars"""
+    import torch
+    n = 1 << 16
+    ref = _ctx(1, 1)
+    s0 = ref.setup_generate(SECRET, n)
+    sets = [util.scalar_stream_bytes(0xE0 + i, n) for i in range(3)] + [util.le(12345678901234567890) * n]
+    expect = [ref.msm_g1(s0, s) for s in sets]
+    ctx = _ctx(2, 2)
+    ctx.set_option("msm_sort", sort)
+    ctx.set_option("msm_window_bits", 14)
+    setup = ctx.setup_generate(SECRET, n)
+    for k, s in enumerate(sets):
+        assert ctx.msm_g1(setup, s) == expect[k], k
+    ts = [ctx.msm_g1_submit(setup, s) for s in sets]
+    for k, t in enumerate(ts):
+        assert ctx.msm_g1_wait(t) == expect[k], k
+    setup.close(); ctx.close(); s0.close(); ref.close()
