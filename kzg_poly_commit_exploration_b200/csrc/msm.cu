@@ -192,30 +192,32 @@ k_digit_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint
 
 // ---- 1-3 in one, two levels: partition sort ----------------------------------------------------------------------
 // The counting sort above pays two GLOBAL atomics per entry (a RED to count, an ATOM to reserve the slot): 21 ps per entry,
-// bound by the L2 atomic units.  Here the buckets are first split into PARTITIONS of 512 consecutive buckets:
+// bound by the L2 atomic units.  Here the buckets are first split into PARTITIONS of 128 consecutive buckets:
 //   k_part_count    per block of 256 scalars a shared-memory histogram over the partitions, then one global RED per
 //                   (block, non-empty partition) instead of one per entry;
 //   k_part_scan     one block: partition bounds;
 //   k_part_scatter  the same histogram again, one global ATOM per (block, partition) reserves the block's range in the
-//                   partition, shared-memory atomics hand out the slots inside it: (bucket mod 512, table index | sign) as
+//                   partition, shared-memory atomics hand out the slots inside it: (bucket mod 128, table index | sign) as
 //                   one 8-byte record per entry, written in runs of ~15 per partition and block;
 //   k_part_sort     one block per partition (~60 k records): histogram of its 512 buckets in shared memory -> their
 //                   bounds (start[]) -> records scattered into the final entry order, all atomics in shared memory.
 // Same contract as the counting sort: start[0..M], vals in bucket order (any order inside a bucket), zero digits vanish.
-// MEASURED (profiles/sweep_coalesce_r02.txt (h), two fused calls at n = 2^20, 31.5 M entries): k_part_count 65 us (the
-// counting sort's count: 214), but k_part_scatter 352 and k_part_sort 304 — the 8-byte records land in runs of ~15 per
-// block and partition, and the final 4-byte scatter of 256 partitions x 492 KB works in a set the size of the L2 — 723 us
-// against 672 for the counting sort.  Kept behind option msm_sort = 2; smaller partitions staged through shared memory
-// would be the next step.
-constexpr int PART_LOG = 9;                     // buckets per partition (log2)
+// MEASURED (profiles/sweep_coalesce_r02.txt (h), two fused calls at n = 2^20, 31.5 M entries): k_part_count 70 us (the
+// counting sort's count: 214) and k_part_sort 116, but k_part_scatter 356 (two recodes, two shared atomics and an 8-byte
+// store per entry at one 1024-thread block per SM) — 545 us against 672 for the counting sort, which four lanes do not
+// see (4.68 vs 4.64 ms per MSM: the 192 KB blocks of k_part_sort share an SM with nobody); a lone call gains 0.05 ms.
+// Kept behind option msm_sort = 2.  (First version, 512-bucket partitions without staging: 65 + 352 + 304 us.)
+constexpr int PART_LOG = 7;                     // buckets per partition (log2)
 constexpr uint32_t PART_W = 1u << PART_LOG;
-constexpr int PART_MAX = 2048;                  // partitions (M <= 2^20 buckets)
+constexpr int PART_MAX = 8192;                  // partitions (M <= 2^20 buckets)
+constexpr int PART_TILE = 1024;                 // scalars per block of the two passes over the scalars
+constexpr uint32_t PART_STAGE = 48 * 1024;      // records of a partition whose final order is staged in shared memory (192 KB)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PART_TILE)
 k_part_count(ScalarPtrs sp, uint64_t n, int c, int W, uint32_t half, uint32_t* __restrict__ part_cnt) {
   __shared__ uint32_t hist[PART_MAX];
   const uint32_t np_call = half >> PART_LOG;                       // partitions of one call
-  for (uint32_t k = threadIdx.x; k < np_call; k += 256) hist[k] = 0;
+  for (uint32_t k = threadIdx.x; k < np_call; k += PART_TILE) hist[k] = 0;
   __syncthreads();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -231,17 +233,18 @@ k_part_count(ScalarPtrs sp, uint64_t n, int c, int W, uint32_t half, uint32_t* _
   }
   __syncthreads();
   part_cnt += (size_t)blockIdx.y * np_call;
-  for (uint32_t k = threadIdx.x; k < np_call; k += 256) if (hist[k]) atomicAdd(part_cnt + k, hist[k]);
+  for (uint32_t k = threadIdx.x; k < np_call; k += PART_TILE) if (hist[k]) atomicAdd(part_cnt + k, hist[k]);
 }
 
-// NP <= PART_MAX counts -> part_start[0..NP] and the scatter cursors; one block of 1024 threads, two counts per thread
+// NP <= PART_MAX counts -> part_start[0..NP] and the scatter cursors; one block of 1024 threads, consecutive counts per thread
 __global__ void __launch_bounds__(1024)
 k_part_scan(const uint32_t* __restrict__ part_cnt, uint32_t NP, uint32_t* __restrict__ part_start, uint32_t* __restrict__ part_cur) {
   __shared__ uint32_t warp_tot[32];
-  const uint32_t a0 = 2 * threadIdx.x < NP ? part_cnt[2 * threadIdx.x] : 0u;
-  const uint32_t a1 = 2 * threadIdx.x + 1 < NP ? part_cnt[2 * threadIdx.x + 1] : 0u;
+  const uint32_t per = (NP + 1023) / 1024, b0 = threadIdx.x * per;
+  uint32_t local = 0;
+  for (uint32_t k = 0; k < per; k++) if (b0 + k < NP) local += part_cnt[b0 + k];
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t inc = a0 + a1;
+  uint32_t inc = local;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += t; }
   if (lane == 31) warp_tot[w] = inc;
@@ -253,18 +256,17 @@ k_part_scan(const uint32_t* __restrict__ part_cnt, uint32_t NP, uint32_t* __rest
     warp_tot[lane] = xi - x;
   }
   __syncthreads();
-  const uint32_t ex = warp_tot[w] + inc - (a0 + a1);
-  if (2 * threadIdx.x < NP) { part_start[2 * threadIdx.x] = ex; part_cur[2 * threadIdx.x] = ex; }
-  if (2 * threadIdx.x + 1 < NP) { part_start[2 * threadIdx.x + 1] = ex + a0; part_cur[2 * threadIdx.x + 1] = ex + a0; }
-  if (threadIdx.x == 1023) part_start[NP] = ex + a0 + a1;      // the last thread's running sum is the grand total
+  uint32_t run = warp_tot[w] + inc - local;
+  for (uint32_t k = 0; k < per; k++) if (b0 + k < NP) { part_start[b0 + k] = run; part_cur[b0 + k] = run; run += part_cnt[b0 + k]; }
+  if (threadIdx.x == 1023) part_start[NP] = run;                  // the last thread's running sum is the grand total
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PART_TILE)
 k_part_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint32_t half,
                uint32_t* __restrict__ part_cur, uint2* __restrict__ rec) {
   __shared__ uint32_t hist[PART_MAX];      // counts, then the block's base inside each partition, then the running slot
   const uint32_t np_call = half >> PART_LOG;
-  for (uint32_t k = threadIdx.x; k < np_call; k += 256) hist[k] = 0;
+  for (uint32_t k = threadIdx.x; k < np_call; k += PART_TILE) hist[k] = 0;
   __syncthreads();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   Fr k;
@@ -281,7 +283,7 @@ k_part_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint3
   }
   __syncthreads();
   part_cur += (size_t)blockIdx.y * np_call;
-  for (uint32_t q = threadIdx.x; q < np_call; q += 256) {
+  for (uint32_t q = threadIdx.x; q < np_call; q += PART_TILE) {
     const uint32_t h = hist[q];
     hist[q] = h ? atomicAdd(part_cur + q, h) : 0u;               // this block's range in partition q starts here
   }
@@ -299,10 +301,13 @@ k_part_scatter(ScalarPtrs sp, uint64_t n, int c, int W, uint64_t n_stride, uint3
   }
 }
 
-// one block per partition: records [part_start[P], part_start[P+1]) -> start[P * 512 .. ] and vals in bucket order
+// one block per partition: records [part_start[P], part_start[P+1]) -> start[P * 128 .. ] and vals in bucket order.  A
+// partition of up to PART_STAGE records gets its final order in shared memory and leaves in one coalesced copy (random
+// 4-byte stores to global memory cost a 32-byte sector each); a larger one (skewed scalars) is scattered directly.
 __global__ void __launch_bounds__(1024)
 k_part_sort(const uint2* __restrict__ rec, const uint32_t* __restrict__ part_start, uint32_t NP,
             uint32_t* __restrict__ start, uint32_t* __restrict__ vals) {
+  extern __shared__ uint32_t stage[];           // PART_STAGE words
   __shared__ uint32_t cnt[PART_W];
   __shared__ uint32_t warp_tot[32];
   const uint32_t P = blockIdx.x;
@@ -311,7 +316,7 @@ k_part_sort(const uint2* __restrict__ rec, const uint32_t* __restrict__ part_sta
   __syncthreads();
   for (uint32_t e = lo + threadIdx.x; e < hi; e += 1024) atomicAdd(&cnt[rec[e].y], 1u);
   __syncthreads();
-  // exclusive scan of the 512 counts by the first 512 threads (16 warps)
+  // exclusive scan of the 128 counts by the first four warps
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t own = threadIdx.x < PART_W ? cnt[threadIdx.x] : 0u, inc = own;
 #pragma unroll
@@ -325,16 +330,26 @@ k_part_sort(const uint2* __restrict__ rec, const uint32_t* __restrict__ part_sta
     warp_tot[lane] = xi - x;
   }
   __syncthreads();
+  const bool staged = hi - lo <= PART_STAGE;
   if (threadIdx.x < PART_W) {
-    const uint32_t ex = lo + warp_tot[w] + inc - own;
-    start[(size_t)P * PART_W + threadIdx.x] = ex;
-    cnt[threadIdx.x] = ex;                                       // running slot of the bucket
+    const uint32_t ex = warp_tot[w] + inc - own;                 // position inside the partition
+    start[(size_t)P * PART_W + threadIdx.x] = lo + ex;
+    cnt[threadIdx.x] = staged ? ex : lo + ex;                    // running slot of the bucket
   }
   if (P == NP - 1 && threadIdx.x == 0) start[(size_t)NP * PART_W] = hi;
   __syncthreads();
-  for (uint32_t e = lo + threadIdx.x; e < hi; e += 1024) {
-    const uint2 r = rec[e];
-    vals[atomicAdd(&cnt[r.y], 1u)] = r.x;
+  if (staged) {
+    for (uint32_t e = lo + threadIdx.x; e < hi; e += 1024) {
+      const uint2 r = rec[e];
+      stage[atomicAdd(&cnt[r.y], 1u)] = r.x;
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < hi - lo; e += 1024) vals[lo + e] = stage[e];
+  } else {
+    for (uint32_t e = lo + threadIdx.x; e < hi; e += 1024) {
+      const uint2 r = rec[e];
+      vals[atomicAdd(&cnt[r.y], 1u)] = r.x;
+    }
   }
 }
 
@@ -354,15 +369,16 @@ static int32_t launch_part_sort(kzg_ctx* ctx, const ScalarPtrs& sp, int B, uint6
   uint32_t* part_cnt = reinterpret_cast<uint32_t*>(pc);
   uint32_t* part_start = part_cnt + NP + 4;
   uint32_t* part_cur = part_start + NP + 4;
+  KZG_CUDA_OK(ctx, cudaFuncSetAttribute(k_part_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PART_STAGE * 4)));   // per device
   KZG_CUDA_OK(ctx, cudaMemsetAsync(part_cnt, 0, (size_t)NP * 4, ctx->stream));
-  const dim3 grid(blocks_for(n, 256), (unsigned)B);
-  k_part_count<<<grid, 256, 0, ctx->stream>>>(sp, n, c, W, half, part_cnt);
+  const dim3 grid(blocks_for(n, PART_TILE), (unsigned)B);
+  k_part_count<<<grid, PART_TILE, 0, ctx->stream>>>(sp, n, c, W, half, part_cnt);
   KZG_LAUNCHED(ctx);
   k_part_scan<<<1, 1024, 0, ctx->stream>>>(part_cnt, NP, part_start, part_cur);
   KZG_LAUNCHED(ctx);
-  k_part_scatter<<<grid, 256, 0, ctx->stream>>>(sp, n, c, W, n_stride, half, part_cur, reinterpret_cast<uint2*>(rc));
+  k_part_scatter<<<grid, PART_TILE, 0, ctx->stream>>>(sp, n, c, W, n_stride, half, part_cur, reinterpret_cast<uint2*>(rc));
   KZG_LAUNCHED(ctx);
-  k_part_sort<<<NP, 1024, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(rc), part_start, NP, start, vals);
+  k_part_sort<<<NP, 1024, PART_STAGE * 4, ctx->stream>>>(reinterpret_cast<const uint2*>(rc), part_start, NP, start, vals);
   KZG_LAUNCHED(ctx);
   return KZG_OK;
 }
