@@ -550,8 +550,9 @@ int32_t reserve_call(kzg_ctx* ctx, const kzg_setup* s, const void* scalars, uint
     KZG_CUDA_OK(ctx, cudaMemsetAsync(q->scalars, 0x5a, n * 32, lane->stream));
     sc = reinterpret_cast<const uint8_t*>(q->scalars);
   }
-  void* r;
+  void *r, *o;
   KZG_TRY(scratch_get(lane, SCR_MISC, 1024, &r));
+  KZG_TRY(scratch_get(lane, SCR_OUT, 64 * KZG_MAX_COALESCE, &o));      // the launch writes its compressed results there
   int32_t st = msm_any(lane, s, sc, n, reinterpret_cast<G1Xyzz*>(r));
   if (st == KZG_OK) st = finalize_points(lane, reinterpret_cast<G1Xyzz*>(r), 1, reinterpret_cast<uint8_t*>(q->result) + 256);
   if (st != KZG_OK) { if (lane != ctx) ctx->err = lane->err; return st; }
