@@ -429,10 +429,11 @@ k_sum_coop(const G1Xyzz* __restrict__ in, uint64_t count, G1Xyzz* __restrict__ o
 // straight into rank r's mailbox (peer memory mapped through CUDA IPC, NVLink 5 / NVSwitch), publishes it with a
 // release store of the call's sequence number, then spins (acquire loads) on its own mailbox until all `world`
 // partials of this call have landed; the four warps fold them with cooperative additions and thread 0 converts to
-// affine and compresses.  Mailbox slots are KZG_P2P_DEPTH = 2 L deep (L = KZG_MAX_LANES), indexed by the call number: a
-// rank has at most L calls in flight (submit k + L only after waiting for k), k completes on a rank only when EVERY rank
-// has published k, and a rank publishes k only after it finished k - L; so when call k + L overwrites the slot of call
-// k - L every rank is done reading it.  A bounded spin (20 s by default, option p2p_timeout_ms, counted with the device's
+// affine and compresses.  Mailbox slots are KZG_P2P_DEPTH = 2 F deep (F = KZG_MAX_INFLIGHT = lanes x fused calls: the
+// tickets a rank can have out), indexed by the call number: a rank submits k + F only after waiting for k, k completes on
+// a rank only when EVERY rank has published k, and a rank publishes k only after it finished k - F; so when call k + F
+// overwrites the slot of call k - F every rank is done reading it.  The collective calls of a fused group are the blocks
+// of ONE launch (block b = call seq + b, its own slot).  A bounded spin (20 s by default, option p2p_timeout_ms, counted with the device's
 // own clock rate) turns a dead peer into an error instead of a hang, and that error is COLLECTIVE: the rank that gives
 // up writes a sticky word into every peer's mailbox, peers check it while they wait and once more before they return,
 // and the contexts refuse further collective calls (their sequence numbers are no longer in step).
