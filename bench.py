@@ -464,6 +464,7 @@ def msm_headline(args, R, pkg, synthetic, ctx, devices):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": f"single G1 commit-MSM n=2^{LOG_N} (BASELINE config C3), uniform scalars U(0xC3,i), bench-secret setup",
                    "mode": mode, "window_bits": plan["c"], "windows": plan["W"], "halving_rounds": rounds,
+                   "halving_rounds_note": "of a call on its own; fused calls count their entries together (one round more per doubling)",
                    "sharding": f"point range, {per_dev} points/GPU",
                    "exchange": ("none" if n_gpus == 1 else "peer stores over NVLink + fold + compress in one kernel (k_exchange_combine)"),
                    "l2": f"inputs larger than L2 (table {plan['W'] * per_dev * plan['table_pitch'] / 2**20:.0f} MiB + scalars {per_dev * 32 / 2**20:.0f} MiB per GPU)",
