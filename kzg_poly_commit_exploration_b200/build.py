@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkzg_b200.so")
-SOURCES = ["abi.cu", "engine_one.cu", "host_helpers.cu", "poly.cu", "setup.cu", "setup_g2.cu", "g2_import.cu", "pairing.cu", "msm.cu", "msm_tail.cu", "msm_tree.cu", "batch.cu", "batch_tree.cu", "probe.cu"]
+SOURCES = ["abi.cu", "engine_one.cu", "host_helpers.cu", "poly.cu", "setup.cu", "setup_g2.cu", "g2_import.cu", "pairing.cu", "msm.cu", "msm_tail.cu", "msm_tree.cu", "msm_tree_r1.cu", "batch.cu", "batch_tree.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -74,6 +74,7 @@ struct kzg_ctx {
                                        // (measured at n = 2^17 .. 2^18, the per-GPU share of a sharded 2^20 MSM)
   int opt_tree_k = 0;                  // pairs per thread in the halving rounds: 0 = auto (fill the last wave), else 8..16
   int opt_coop_tail = 1;               // 4-warp cooperative additions in the bucket-reduction tail
+  int opt_tree_r1_ool = 0;             // round-1 pair additions from the translation unit with the product out of line (msm_tree_r1.cu)
   int opt_den_side = 0;                // round-1 denominators of calls in flight as this many resident blocks per SM on a high-priority side stream (0 = off)
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_ev[2] = {nullptr, nullptr};

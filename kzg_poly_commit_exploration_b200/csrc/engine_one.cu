@@ -243,6 +243,7 @@ int32_t one_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
   else if (n == "coop_tail") ctx->opt_coop_tail = (int)value;
   else if (n == "reduce_lk") ctx->opt_reduce_lk = (int)value;
   else if (n == "msm_l2") ctx->opt_msm_l2 = (int)value;
+  else if (n == "tree_r1_ool") ctx->opt_tree_r1_ool = (int)value;
   else if (n == "den_side") ctx->opt_den_side = (int)std::min<int64_t>(8, std::max<int64_t>(0, value));
   else if (n == "l2_rounds") ctx->opt_l2_rounds = (int)value;
   else if (n == "tree_k") ctx->opt_tree_k = (int)value;
@@ -475,7 +476,7 @@ void copy_options(kzg_ctx* dst, const kzg_ctx* src) {
   dst->opt_tree_min_pairs = src->opt_tree_min_pairs; dst->opt_inv_top_fan = src->opt_inv_top_fan; dst->opt_inv_top = src->opt_inv_top;
   dst->opt_msm_tree_rounds = src->opt_msm_tree_rounds; dst->opt_acc_min_entries = src->opt_acc_min_entries;
   dst->opt_fixed_table_max_bytes = src->opt_fixed_table_max_bytes; dst->opt_setup_layout = src->opt_setup_layout;
-  dst->opt_setup_tree_min = src->opt_setup_tree_min; dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_reduce_lk = src->opt_reduce_lk; dst->opt_msm_l2 = src->opt_msm_l2; dst->opt_den_side = src->opt_den_side; dst->opt_l2_rounds = src->opt_l2_rounds; dst->opt_acc_minblocks = src->opt_acc_minblocks;
+  dst->opt_setup_tree_min = src->opt_setup_tree_min; dst->opt_tree_k = src->opt_tree_k; dst->opt_coop_tail = src->opt_coop_tail; dst->opt_reduce_lk = src->opt_reduce_lk; dst->opt_msm_l2 = src->opt_msm_l2; dst->opt_tree_r1_ool = src->opt_tree_r1_ool; dst->opt_den_side = src->opt_den_side; dst->opt_l2_rounds = src->opt_l2_rounds; dst->opt_acc_minblocks = src->opt_acc_minblocks;
 }
 
 static void latch_queue(kzg_ctx* ctx) {

@@ -7,7 +7,7 @@ fn main() {
     let mut objs = vec![];
     // the same list as kzg_poly_commit_exploration_b200/build.py SOURCES
     for f in ["abi.cu", "engine_one.cu", "host_helpers.cu", "poly.cu", "setup.cu", "setup_g2.cu", "g2_import.cu", "pairing.cu", "msm.cu", "msm_tail.cu",
-              "msm_tree.cu", "batch.cu", "batch_tree.cu", "probe.cu"] {
+              "msm_tree.cu", "msm_tree_r1.cu", "batch.cu", "batch_tree.cu", "probe.cu"] {
         let obj = out.join(f.replace(".cu", ".o"));
         let st = Command::new("nvcc")
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c"])
